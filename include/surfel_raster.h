@@ -1,0 +1,150 @@
+/*
+ * surfel_raster.h -- C ABI of the B200-native Gaussian-surfel rasterizer.
+ *
+ * This is the drop-in boundary for the hot path of yikaiw/Vidu4D's Stage-3
+ * ("dynamic Gaussian surfels"): it replaces
+ *
+ *     CudaRasterizer::Rasterizer::forward      RAST/cuda_rasterizer/rasterizer.h:33-59
+ *     CudaRasterizer::Rasterizer::backward     RAST/cuda_rasterizer/rasterizer.h:61-87
+ *     CudaRasterizer::Rasterizer::markVisible  RAST/cuda_rasterizer/rasterizer.h:25-31
+ *
+ * (RAST = gs/submodules/diff-surfel-rasterization) which the reference reaches
+ * through its pybind module `_C` (RAST/ext.cpp:15-19, RAST/rasterize_points.cu:39-261).
+ * Plain pointers and sizes only -- no torch types.  All pointers are DEVICE
+ * pointers unless stated; `stream` is a cudaStream_t passed as void* (NULL = the
+ * legacy default stream, which is what the reference always uses).
+ *
+ * Differences from the reference interface, on purpose:
+ *   - The reference grows its three scratch buffers through std::function
+ *     callbacks and blocks on a D2H copy of `num_rendered` in the middle of
+ *     forward() (rasterizer_impl.cu:282).  Here the caller sizes the buffers up
+ *     front with the sr_*_bytes() queries; the instance buffer has a CAPACITY and
+ *     forward() never synchronises: `num_rendered` lands in a caller-supplied
+ *     (pinned) host word asynchronously.  If the capacity is too small the frame
+ *     is not rendered and SR_STATUS_OVERFLOW is reported through `status`
+ *     (see sr_forward()).
+ *   - `transMat_precomp` ("cov3D_precomp" at the Python level) is rejected: the
+ *     reference's own path for it leaves the normal uninitialised
+ *     (forward.cu:214-218) and nothing in Vidu4D uses it.
+ *   - The opaque buffer layouts are ours ("HBM layout"); use
+ *     sr_debug_view() to look inside them in tests.
+ *
+ * Every function returns 0 on success, a negative SR_E* code on error;
+ * sr_last_error() returns a human-readable message for the calling thread.
+ */
+#ifndef SURFEL_RASTER_H_
+#define SURFEL_RASTER_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SR_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define SR_API __attribute__((visibility("default")))
+#else
+#define SR_API
+#endif
+
+#define SR_EINVAL   (-1)   /* bad argument (shape, null pointer, unsupported option) */
+#define SR_ECUDA    (-2)   /* a CUDA runtime call or launch failed */
+#define SR_ECAPACITY (-3)  /* instance capacity exceeded (only from the synchronous helpers) */
+
+/* bits of the device/host status word written by sr_forward() */
+#define SR_STATUS_OK        0u
+#define SR_STATUS_OVERFLOW  1u   /* num_rendered > capacity: nothing was binned or composited */
+
+/* One frame's static description (GaussianRasterizationSettings,
+ * RAST/diff_surfel_rasterization/__init__.py:158-170, plus P/M). */
+typedef struct sr_frame {
+    int32_t P;             /* number of surfels */
+    int32_t sh_degree;     /* active SH degree D (0..3) */
+    int32_t sh_coeffs;     /* M = shs.size(1); 0 when colors_precomp is used */
+    int32_t width, height;
+    float   tan_fovx, tan_fovy;
+    float   scale_modifier;  /* accepted and ignored, exactly like the reference (forward.cu:95) */
+    int32_t prefiltered;     /* if set, a culled surfel is an error in the reference (__trap); we report it via status bit 2 */
+    int32_t debug;           /* if set, synchronise + check after every launch (auxiliary.h:271-278) */
+} sr_frame;
+
+/* ---- buffer sizing (replaces required<GeometryState/ImageState/BinningState>, rasterizer_impl.h:66-72) */
+SR_API size_t sr_geom_bytes(int32_t P);
+SR_API size_t sr_image_bytes(int32_t width, int32_t height);
+SR_API size_t sr_binning_bytes(int64_t capacity /* max instances */, int32_t width, int32_t height);
+
+/*
+ * Forward.  Replaces Rasterizer::forward (rasterizer_impl.cu:198-342).
+ *
+ *   background[3], means3D[P*3], shs[P*M*3] | colors_precomp[P*3] (exactly one non-NULL),
+ *   opacities[P], scales[P*2], rotations[P*4] (w,x,y,z), viewmatrix[16], projmatrix[16], campos[3]
+ *   out_color[3*H*W], out_others[8*H*W], radii[P] (int32)           -- written
+ *   geom/binning/image buffers: caller-allocated, sizes from sr_*_bytes()
+ *   capacity: number of instances the binning buffer was sized for
+ *   num_rendered_dev: device uint32[2] -> {num_rendered, status}; also copied
+ *       asynchronously to num_rendered_host (pinned host uint32[2]) if non-NULL.
+ */
+SR_API int sr_forward(const sr_frame* f,
+               const float* background, const float* means3D, const float* shs,
+               const float* colors_precomp, const float* opacities, const float* scales,
+               const float* rotations, const float* viewmatrix, const float* projmatrix,
+               const float* campos,
+               float* out_color, float* out_others, int32_t* radii,
+               void* geom_buffer, void* binning_buffer, void* image_buffer, int64_t capacity,
+               uint32_t* num_rendered_dev, uint32_t* num_rendered_host, void* stream);
+
+/*
+ * Backward.  Replaces Rasterizer::backward (rasterizer_impl.cu:346-448).
+ * Inputs as in forward plus dL_dout_color[3*H*W], dL_dout_others[8*H*W] and the
+ * three buffers the forward filled.  Outputs (all fully written, no need to zero):
+ *   dL_dmeans2D[P*3] (the densification proxy of backward.cu:645-648; z = 0),
+ *   dL_dcolors[P*3], dL_dopacity[P], dL_dmeans3D[P*3], dL_dtransMat[P*9],
+ *   dL_dsh[P*M*3], dL_dscales[P*2], dL_drotations[P*4]
+ */
+SR_API int sr_backward(const sr_frame* f,
+                const float* background, const float* means3D, const float* shs,
+                const float* colors_precomp, const float* scales, const float* rotations,
+                const float* viewmatrix, const float* projmatrix, const float* campos,
+                const int32_t* radii,
+                const float* dL_dout_color, const float* dL_dout_others,
+                void* geom_buffer, void* binning_buffer, void* image_buffer, int64_t capacity,
+                float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity, float* dL_dmeans3D,
+                float* dL_dtransMat, float* dL_dsh, float* dL_dscales, float* dL_drotations,
+                void* stream);
+
+/* Replaces Rasterizer::markVisible (rasterizer_impl.cu:141-153): present[i] = p_view.z > 0.2 */
+SR_API int sr_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                    uint8_t* present, void* stream);
+
+/* ---- introspection for tests: byte offsets of the sub-arrays inside our opaque buffers */
+typedef struct sr_debug_layout {
+    /* geometry buffer (per surfel) */
+    size_t surfel_rec;      /* float[P*20]  packed record, see DESIGN.md */
+    size_t depths;          /* float[P]     view-space z (sort key low word) */
+    size_t tiles_touched;   /* uint32[P] */
+    size_t point_offsets;   /* uint32[P]    inclusive scan of tiles_touched */
+    size_t clamped;         /* uint8[P]     bit c set = colour channel c clamped at 0 */
+    /* binning buffer (per instance); the sorted arrays live in ping or pong: read `sorted_sel` first */
+    size_t keys[2];         /* uint64[capacity] x2 */
+    size_t values[2];       /* uint32[capacity] x2 */
+    size_t sort_ctl;        /* uint32[..]: [0]=sorted_sel (0/1) after forward */
+    size_t inst_rec;        /* float[capacity*20] per-instance record stream */
+    /* image buffer */
+    size_t final_T;         /* float[3*N]  T, M1, M2 */
+    size_t n_contrib;       /* uint32[2*N] last, median */
+    size_t ranges;          /* uint32[tiles*2] */
+} sr_debug_layout;
+SR_API int sr_debug_view(int32_t P, int32_t width, int32_t height, int64_t capacity, sr_debug_layout* out);
+
+SR_API int sr_abi_version(void);
+SR_API const char* sr_last_error(void);
+/* number of kernel launches issued by this library since load (bench.py's `gpu_launches`) */
+SR_API uint64_t sr_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SURFEL_RASTER_H_ */

@@ -1,0 +1,94 @@
+"""ctypes binding of vidu4d_b200/lib/libsurfel_raster.so (include/surfel_raster.h).
+
+The CUDA library is the product; there is NO fallback.  If the library is missing or does not
+export the declared ABI this module raises at first use -- it never routes to a CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libsurfel_raster.so")
+
+ABI_VERSION = 1
+SR_STATUS_OVERFLOW = 1
+SR_STATUS_PREFILTER = 4
+
+SYMBOLS = (
+    "sr_geom_bytes", "sr_image_bytes", "sr_binning_bytes", "sr_forward", "sr_backward",
+    "sr_mark_visible", "sr_debug_view", "sr_abi_version", "sr_last_error", "sr_launch_count",
+)
+
+
+class SrFrame(C.Structure):
+    _fields_ = [
+        ("P", C.c_int32), ("sh_degree", C.c_int32), ("sh_coeffs", C.c_int32),
+        ("width", C.c_int32), ("height", C.c_int32),
+        ("tan_fovx", C.c_float), ("tan_fovy", C.c_float), ("scale_modifier", C.c_float),
+        ("prefiltered", C.c_int32), ("debug", C.c_int32),
+    ]
+
+
+class SrDebugLayout(C.Structure):
+    _fields_ = [
+        ("surfel_rec", C.c_size_t), ("depths", C.c_size_t), ("tiles_touched", C.c_size_t),
+        ("point_offsets", C.c_size_t), ("clamped", C.c_size_t),
+        ("keys", C.c_size_t * 2), ("values", C.c_size_t * 2), ("sort_ctl", C.c_size_t),
+        ("inst_rec", C.c_size_t),
+        ("final_T", C.c_size_t), ("n_contrib", C.c_size_t), ("ranges", C.c_size_t),
+    ]
+
+
+class SurfelRasterError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load the CUDA library; raise loudly if it is absent (run `python -m vidu4d_b200.build`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SurfelRasterError(
+            f"{LIB_PATH} not found: the CUDA extension is not built. Run `python -m vidu4d_b200.build` "
+            "(or __graft_entry__.build()). There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for s in SYMBOLS:
+        if not hasattr(lib, s):
+            raise SurfelRasterError(f"{LIB_PATH} does not export {s}")
+    vp, i32, i64, f32p = C.c_void_p, C.c_int32, C.c_int64, C.c_void_p
+    lib.sr_abi_version.restype = C.c_int
+    lib.sr_last_error.restype = C.c_char_p
+    lib.sr_launch_count.restype = C.c_uint64
+    lib.sr_geom_bytes.restype = C.c_size_t
+    lib.sr_geom_bytes.argtypes = [i32]
+    lib.sr_image_bytes.restype = C.c_size_t
+    lib.sr_image_bytes.argtypes = [i32, i32]
+    lib.sr_binning_bytes.restype = C.c_size_t
+    lib.sr_binning_bytes.argtypes = [i64, i32, i32]
+    lib.sr_forward.restype = C.c_int
+    lib.sr_forward.argtypes = [C.POINTER(SrFrame)] + [f32p] * 10 + [vp, vp, vp] + [vp, vp, vp, i64, vp, vp, vp]
+    lib.sr_backward.restype = C.c_int
+    lib.sr_backward.argtypes = [C.POINTER(SrFrame)] + [f32p] * 9 + [vp] + [f32p] * 2 + [vp, vp, vp, i64] + [f32p] * 8 + [vp]
+    lib.sr_mark_visible.restype = C.c_int
+    lib.sr_mark_visible.argtypes = [i32, f32p, f32p, f32p, vp, vp]
+    lib.sr_debug_view.restype = C.c_int
+    lib.sr_debug_view.argtypes = [i32, i32, i32, i64, C.POINTER(SrDebugLayout)]
+    if lib.sr_abi_version() != ABI_VERSION:
+        raise SurfelRasterError(f"ABI mismatch: library {lib.sr_abi_version()} != binding {ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load().sr_last_error().decode("utf-8", "replace")
+        raise SurfelRasterError(f"{what} failed (code {rc}): {msg}")
+
+
+def launch_count() -> int:
+    return int(load().sr_launch_count())

@@ -1,0 +1,194 @@
+// api.cu -- the C ABI declared in include/surfel_raster.h: argument checking, buffer layout,
+// launch orchestration.  Replaces the host side of the reference:
+//   Rasterizer::forward / backward / markVisible   RAST/cuda_rasterizer/rasterizer_impl.cu:141-153,198-342,346-448
+//   GeometryState/ImageState/BinningState::fromChunk, required<T>   rasterizer_impl.cu:155-194, rasterizer_impl.h:66-72
+// No torch types; no host<->device synchronisation on the forward/backward path (debug mode excepted).
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace {
+thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* where) {
+    return fail(SR_ECUDA, "CUDA error in %s: %s", where, cudaGetErrorString(e));
+}
+#define CK(call, where)                                      \
+    do {                                                     \
+        cudaError_t e_ = (call);                             \
+        if (e_ != cudaSuccess) return cuda_fail(e_, where);  \
+    } while (0)
+#define DBG(where)                                           \
+    do {                                                     \
+        if (debug) CK(cudaStreamSynchronize(stream), where); \
+    } while (0)
+
+CamParams make_cam(const sr_frame* f, const float* vm, const float* campos, const float* bg) {
+    CamParams c{};
+    c.vm = vm; c.campos = campos; c.bg = bg;
+    c.W = f->width; c.H = f->height;
+    c.tiles_x = (f->width + SR_TILE - 1) / SR_TILE;
+    c.tiles_y = (f->height + SR_TILE - 1) / SR_TILE;
+    c.P = f->P; c.D = f->sh_degree; c.M = f->sh_coeffs;
+    // rasterizer_impl.cu:223-224
+    c.focal_y = f->height / (2.0f * f->tan_fovy);
+    c.focal_x = f->width / (2.0f * f->tan_fovx);
+    // forward.cu:208  {focal_x, focal_y, float(W)/2.0, float(H)/2.0}
+    c.cx = (float)((float)f->width / 2.0);
+    c.cy = (float)((float)f->height / 2.0);
+    // backward.cu:570 / 683-684
+    c.bcx = c.focal_x * f->tan_fovx;
+    c.bcy = c.focal_y * f->tan_fovy;
+    return c;
+}
+
+int check_frame(const sr_frame* f) {
+    if (!f) return fail(SR_EINVAL, "frame descriptor is NULL");
+    if (f->P < 0) return fail(SR_EINVAL, "P must be >= 0");
+    if (f->width <= 0 || f->height <= 0) return fail(SR_EINVAL, "image size must be positive");
+    if (f->width > 65535 || f->height > 65535) return fail(SR_EINVAL, "image side must be < 65536");
+    if (f->sh_degree < 0 || f->sh_degree > 3) return fail(SR_EINVAL, "sh_degree must be 0..3");
+    if (f->sh_coeffs < 0) return fail(SR_EINVAL, "sh_coeffs must be >= 0");
+    if (f->sh_coeffs > 0 && (f->sh_degree + 1) * (f->sh_degree + 1) > f->sh_coeffs)
+        return fail(SR_EINVAL, "sh_degree %d needs %d coefficients, shs has %d", f->sh_degree,
+                    (f->sh_degree + 1) * (f->sh_degree + 1), f->sh_coeffs);
+    return 0;
+}
+}  // namespace
+
+void sr_count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+extern "C" {
+
+int sr_abi_version(void) { return SR_ABI_VERSION; }
+const char* sr_last_error(void) { return g_err; }
+uint64_t sr_launch_count(void) { return g_launches.load(); }
+
+size_t sr_geom_bytes(int32_t P) { return geom_layout(P).total; }
+size_t sr_image_bytes(int32_t width, int32_t height) { return image_layout(width, height).total; }
+size_t sr_binning_bytes(int64_t capacity, int32_t, int32_t) { return bin_layout(capacity).total; }
+
+int sr_debug_view(int32_t P, int32_t width, int32_t height, int64_t capacity, sr_debug_layout* out) {
+    if (!out) return fail(SR_EINVAL, "out is NULL");
+    const GeomLayout g = geom_layout(P);
+    const ImageLayout i = image_layout(width, height);
+    const BinLayout b = bin_layout(capacity);
+    out->surfel_rec = g.surfel_rec; out->depths = g.depths; out->tiles_touched = g.tiles_touched;
+    out->point_offsets = g.point_offsets; out->clamped = g.clamped;
+    out->keys[0] = b.keys[0]; out->keys[1] = b.keys[1]; out->values[0] = b.values[0]; out->values[1] = b.values[1];
+    out->sort_ctl = b.sort_ctl; out->inst_rec = b.inst_rec;
+    out->final_T = i.final_T; out->n_contrib = i.n_contrib; out->ranges = i.ranges;
+    return 0;
+}
+
+int sr_forward(const sr_frame* f, const float* background, const float* means3D, const float* shs,
+               const float* colors_precomp, const float* opacities, const float* scales, const float* rotations,
+               const float* viewmatrix, const float* projmatrix, const float* campos, float* out_color,
+               float* out_others, int32_t* radii, void* geom_buffer, void* binning_buffer, void* image_buffer,
+               int64_t capacity, uint32_t* num_rendered_dev, uint32_t* num_rendered_host, void* stream_) {
+    (void)projmatrix;   // only feeds dead code in the reference (auxiliary.h:170-172)
+    if (int rc = check_frame(f)) return rc;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const bool debug = f->debug != 0;
+    const int P = f->P;
+    const size_t N = (size_t)f->width * f->height;
+    if (!out_color || !out_others || !num_rendered_dev) return fail(SR_EINVAL, "output pointer is NULL");
+    if (!background || !viewmatrix || !campos) return fail(SR_EINVAL, "camera / background pointer is NULL");
+    CK(cudaMemsetAsync(num_rendered_dev, 0, 2 * sizeof(uint32_t), stream), "memset(num_rendered)");
+    if (P == 0) {
+        // rasterize_points.cu:106 -- P == 0 short-circuits to zero-filled outputs
+        CK(cudaMemsetAsync(out_color, 0, 3 * N * sizeof(float), stream), "memset(out_color)");
+        CK(cudaMemsetAsync(out_others, 0, 8 * N * sizeof(float), stream), "memset(out_others)");
+        if (num_rendered_host)
+            CK(cudaMemcpyAsync(num_rendered_host, num_rendered_dev, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream), "copy(num_rendered)");
+        return 0;
+    }
+    if (!means3D || !opacities || !scales || !rotations || !radii) return fail(SR_EINVAL, "surfel attribute pointer is NULL");
+    if ((shs == nullptr) == (colors_precomp == nullptr))
+        return fail(SR_EINVAL, "provide exactly one of shs / colors_precomp");
+    if (shs && f->sh_coeffs == 0) return fail(SR_EINVAL, "shs given but sh_coeffs == 0");
+    if (!geom_buffer || !binning_buffer || !image_buffer) return fail(SR_EINVAL, "scratch buffer is NULL");
+    if (capacity <= 0 || capacity >= (1ll << 30)) return fail(SR_EINVAL, "capacity must be in (0, 2^30)");
+
+    FwdArgs a{};
+    a.cam = make_cam(f, viewmatrix, campos, background);
+    if (!shs) a.cam.M = 0;
+    a.means3D = means3D; a.shs = shs; a.colors_precomp = colors_precomp; a.opacities = opacities;
+    a.scales = scales; a.rotations = rotations;
+    a.out_color = out_color; a.out_others = out_others; a.radii = radii;
+    a.geom = (char*)geom_buffer; a.bin = (char*)binning_buffer; a.img = (char*)image_buffer;
+    a.gl = geom_layout(P); a.bl = bin_layout(capacity); a.il = image_layout(f->width, f->height);
+    a.num_rendered_dev = num_rendered_dev;
+    a.prefiltered = f->prefiltered;
+    a.key_bits = 32 + (int)sr_higher_msb((uint32_t)a.il.tiles);
+    a.stream = stream; a.debug = debug;
+
+    // one memset clears sort control words, digit histograms and look-back status; one clears ranges+tile_last
+    CK(cudaMemsetAsync(a.bin + a.bl.sort_ctl, 0, a.bl.total - a.bl.sort_ctl, stream), "memset(sort state)");
+    CK(cudaMemsetAsync(a.img + a.il.ranges, 0, a.il.total - a.il.ranges, stream), "memset(ranges)");
+    CK(launch_preprocess_fwd(a), "preprocess_fwd"); DBG("preprocess_fwd");
+    CK(launch_scan_emit(a), "scan/emit_keys"); DBG("scan/emit_keys");
+    CK(launch_sort(a), "sort"); DBG("sort");
+    CK(launch_ranges_gather(a), "ranges_gather"); DBG("ranges_gather");
+    CK(launch_composite_fwd(a), "composite_fwd"); DBG("composite_fwd");
+    if (num_rendered_host)
+        CK(cudaMemcpyAsync(num_rendered_host, num_rendered_dev, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream), "copy(num_rendered)");
+    return 0;
+}
+
+int sr_backward(const sr_frame* f, const float* background, const float* means3D, const float* shs,
+                const float* colors_precomp, const float* scales, const float* rotations, const float* viewmatrix,
+                const float* projmatrix, const float* campos, const int32_t* radii, const float* dL_dout_color,
+                const float* dL_dout_others, void* geom_buffer, void* binning_buffer, void* image_buffer,
+                int64_t capacity, float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity, float* dL_dmeans3D,
+                float* dL_dtransMat, float* dL_dsh, float* dL_dscales, float* dL_drotations, void* stream_) {
+    (void)projmatrix;
+    if (int rc = check_frame(f)) return rc;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const bool debug = f->debug != 0;
+    if (f->P == 0) return 0;   // rasterize_points.cu:204
+    if (!background || !means3D || !scales || !rotations || !viewmatrix || !campos || !radii || !dL_dout_color ||
+        !dL_dout_others || !geom_buffer || !binning_buffer || !image_buffer)
+        return fail(SR_EINVAL, "input pointer is NULL");
+    if (!dL_dmeans2D || !dL_dcolors || !dL_dopacity || !dL_dmeans3D || !dL_dtransMat || !dL_dscales || !dL_drotations)
+        return fail(SR_EINVAL, "gradient output pointer is NULL");
+    if (shs && !dL_dsh) return fail(SR_EINVAL, "dL_dsh is NULL");
+    if (capacity <= 0) return fail(SR_EINVAL, "capacity must be positive");
+
+    BwdArgs a{};
+    a.cam = make_cam(f, viewmatrix, campos, background);
+    if (!shs) a.cam.M = 0;
+    a.means3D = means3D; a.shs = shs; a.colors_precomp = colors_precomp; a.scales = scales; a.rotations = rotations;
+    a.radii = radii; a.dL_dcolor = dL_dout_color; a.dL_dothers = dL_dout_others;
+    a.geom = (char*)geom_buffer; a.bin = (char*)binning_buffer; a.img = (char*)image_buffer;
+    a.gl = geom_layout(f->P); a.bl = bin_layout(capacity); a.il = image_layout(f->width, f->height);
+    a.dL_dmeans2D = dL_dmeans2D; a.dL_dcolors = dL_dcolors; a.dL_dopacity = dL_dopacity; a.dL_dmeans3D = dL_dmeans3D;
+    a.dL_dtransMat = dL_dtransMat; a.dL_dsh = dL_dsh; a.dL_dscales = dL_dscales; a.dL_drotations = dL_drotations;
+    a.stream = stream; a.debug = debug;
+    CK(launch_composite_bwd(a), "composite_bwd"); DBG("composite_bwd");
+    CK(launch_surfel_bwd(a), "surfel_bwd"); DBG("surfel_bwd");
+    return 0;
+}
+
+int sr_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                    uint8_t* present, void* stream_) {
+    (void)projmatrix;
+    if (P < 0) return fail(SR_EINVAL, "P must be >= 0");
+    if (P == 0) return 0;
+    if (!means3D || !viewmatrix || !present) return fail(SR_EINVAL, "pointer is NULL");
+    CK(launch_mark_visible(P, means3D, viewmatrix, present, (cudaStream_t)stream_), "mark_visible");
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,215 @@
+// surfel_bwd.cu -- per-surfel backward: projected-AABB vjp, tangent-plane homography vjp,
+// quaternion / scale vjp and SH vjp, fused into one streaming kernel.
+//
+// Replaces (behaviour, not code) of the reference:
+//   computeAABB (bwd)        RAST/cuda_rasterizer/backward.cu:599-649
+//   preprocessCUDA (bwd)     RAST/cuda_rasterizer/backward.cu:533-597
+//   computeTransMat vjp      RAST/cuda_rasterizer/backward.cu:451-529
+//   quat_to_rotmat_vjp       RAST/cuda_rasterizer/auxiliary.h:213-257
+//   computeColorFromSH (bwd) RAST/cuda_rasterizer/backward.cu:20-139
+//
+// The reference runs two kernels over nine zero-filled P-sized tensors; here one kernel reads the
+// 80-byte per-surfel accumulator written by the composite backward and writes every output tensor
+// exactly once (including the zeros of invisible surfels), so the caller can hand in torch.empty().
+#include "common.cuh"
+
+namespace {
+
+__constant__ float kSH_C0 = 0.28209479177387814f;
+__constant__ float kSH_C1 = 0.4886025119029199f;
+__constant__ float kSH_C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                                -1.0925484305920792f, 0.5462742152960396f};
+__constant__ float kSH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f,
+                                0.3731763325901154f, -0.4570457994644658f, 1.445305721320277f,
+                                -0.5900435899266435f};
+
+struct V3 { float x, y, z; };
+__device__ __forceinline__ V3 wmul(const float* m, V3 v) {      // W * v
+    return {m[0] * v.x + m[4] * v.y + m[8] * v.z, m[1] * v.x + m[5] * v.y + m[9] * v.z, m[2] * v.x + m[6] * v.y + m[10] * v.z};
+}
+__device__ __forceinline__ V3 wtmul(const float* m, V3 v) {     // W^T * v
+    return {m[0] * v.x + m[1] * v.y + m[2] * v.z, m[4] * v.x + m[5] * v.y + m[6] * v.z, m[8] * v.x + m[9] * v.y + m[10] * v.z};
+}
+
+__global__ void __launch_bounds__(256)
+surfel_bwd_kernel(const CamParams c, const float* __restrict__ means3D, const float* __restrict__ shs,
+                  const float2* __restrict__ scales, const float4* __restrict__ rotations, const int* __restrict__ radii,
+                  const float4* __restrict__ srec, const uint8_t* __restrict__ clamped, const float4* __restrict__ sgrad,
+                  float* __restrict__ dL_dmeans2D, float* __restrict__ dL_dcolors, float* __restrict__ dL_dopacity,
+                  float* __restrict__ dL_dmeans3D, float* __restrict__ dL_dtransMat, float* __restrict__ dL_dsh,
+                  float2* __restrict__ dL_dscales, float4* __restrict__ dL_drotations) {
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx >= c.P) return;
+    const int M = c.M;
+    float* osh = dL_dsh + (size_t)idx * M * 3;
+    if (!(radii[idx] > 0)) {
+        // invisible: every gradient is zero (the reference leaves its zero-filled tensors untouched)
+#pragma unroll
+        for (int i = 0; i < 3; i++) { dL_dmeans2D[3 * (size_t)idx + i] = 0.f; dL_dcolors[3 * (size_t)idx + i] = 0.f; dL_dmeans3D[3 * (size_t)idx + i] = 0.f; }
+        dL_dopacity[idx] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 9; i++) dL_dtransMat[9 * (size_t)idx + i] = 0.f;
+        for (int i = 0; i < M * 3; i++) osh[i] = 0.f;
+        dL_dscales[idx] = make_float2(0.f, 0.f);
+        dL_drotations[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
+    float vm[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) vm[i] = __ldg(c.vm + i);
+    const float4* g4 = sgrad + (size_t)idx * 5;
+    const float4 g0 = g4[0], g1 = g4[1], g2 = g4[2], g3 = g4[3], g4v = g4[4];
+    float dT[9] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w, g2.x};
+    const float dmx = g2.y, dmy = g2.z, dop = g2.w;
+    const float dcol[3] = {g3.x, g3.y, g3.z};
+    const float dnr[3] = {g3.w, g4v.x, g4v.y};
+    const float4* r4 = srec + (size_t)idx * 5;
+    const float4 r0 = __ldg(r4), r1 = __ldg(r4 + 1), r2 = __ldg(r4 + 2);
+    const float T[9] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x};
+
+    // ---- computeAABB vjp (backward.cu:599-649): dL/dcentre -> dL/dT ----
+    {
+        const float d = T[6] * T[6] + T[7] * T[7] - T[8] * T[8];
+        const float inv = 1.0f / d;
+        const float f[3] = {inv, inv, -inv};
+        float dL_dT3[3], dL_df[3];
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            dT[i] += dmx * f[i] * T[6 + i];
+            dT[3 + i] += dmy * f[i] * T[6 + i];
+            dL_dT3[i] = dmx * f[i] * T[i] + dmy * f[i] * T[3 + i];
+            dL_df[i] = dmx * T[i] * T[6 + i] + dmy * T[3 + i] * T[6 + i];
+        }
+        const float dL_dd = (dL_df[0] * f[0] + dL_df[1] * f[1] + dL_df[2] * f[2]) * (-1.0f / d);
+        dT[6] += dL_dT3[0] + dL_dd * (2.0f * T[6]);
+        dT[7] += dL_dT3[1] + dL_dd * (2.0f * T[7]);
+        dT[8] += dL_dT3[2] + dL_dd * (-2.0f * T[8]);
+    }
+#pragma unroll
+    for (int i = 0; i < 9; i++) dL_dtransMat[9 * (size_t)idx + i] = dT[i];
+    // densification proxy that the reference stores into dL_dmean2D (backward.cu:645-648)
+    dL_dmeans2D[3 * (size_t)idx + 0] = dT[2] * T[8] * c.bcx;
+    dL_dmeans2D[3 * (size_t)idx + 1] = dT[5] * T[8] * c.bcy;
+    dL_dmeans2D[3 * (size_t)idx + 2] = 0.f;
+    dL_dopacity[idx] = dop;
+#pragma unroll
+    for (int i = 0; i < 3; i++) dL_dcolors[3 * (size_t)idx + i] = dcol[i];
+
+    // ---- computeTransMat vjp (backward.cu:451-529) ----
+    const float4 q = __ldg(rotations + idx);
+    const float2 sc = __ldg(scales + idx);
+    const float sN = rsqrtf(q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z);
+    const float w = q.x * sN, x = q.y * sN, y = q.z * sN, z = q.w * sN;
+    // column-major R of the normalised quaternion
+    const float R[9] = {1.f - 2.f * (y * y + z * z), 2.f * (x * y + w * z), 2.f * (x * z - w * y),
+                        2.f * (x * y - w * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z + w * x),
+                        2.f * (x * z + w * y), 2.f * (y * z - w * x), 1.f - 2.f * (x * x + y * y)};
+    const V3 p = {__ldg(means3D + 3 * (size_t)idx), __ldg(means3D + 3 * (size_t)idx + 1), __ldg(means3D + 3 * (size_t)idx + 2)};
+    V3 pv = wmul(vm, p);
+    pv.x += vm[12]; pv.y += vm[13]; pv.z += vm[14];
+    // dL_dM column j = K^T (dTu[j], dTv[j], dTw[j]) with the BACKWARD intrinsics (cx = focal*tanfov)
+    V3 dM[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        dM[j].x = c.focal_x * dT[j];
+        dM[j].y = c.focal_y * dT[3 + j];
+        dM[j].z = c.bcx * dT[j] + c.bcy * dT[3 + j] + dT[6 + j];
+    }
+    const V3 dRS0 = wtmul(vm, dM[0]), dRS1 = wtmul(vm, dM[1]), dpw = wtmul(vm, dM[2]);
+    V3 dtn = wtmul(vm, V3{dnr[0], dnr[1], dnr[2]});
+    const V3 tn = wmul(vm, V3{R[6], R[7], R[8]});
+    const float cosv = -tn.x * pv.x - tn.y * pv.y - tn.z * pv.z;
+    const float mult = cosv > 0.f ? 1.f : -1.f;
+    dtn.x *= mult; dtn.y *= mult; dtn.z *= mult;
+    // v_R[col][row]
+    const float vR[3][3] = {{dRS0.x * sc.x, dRS0.y * sc.x, dRS0.z * sc.x},
+                            {dRS1.x * sc.y, dRS1.y * sc.y, dRS1.z * sc.y},
+                            {dtn.x, dtn.y, dtn.z}};
+    float4 dq;
+    dq.x = 2.f * (x * (vR[1][2] - vR[2][1]) + y * (vR[2][0] - vR[0][2]) + z * (vR[0][1] - vR[1][0]));
+    dq.y = 2.f * (-2.f * x * (vR[1][1] + vR[2][2]) + y * (vR[0][1] + vR[1][0]) + z * (vR[0][2] + vR[2][0]) + w * (vR[1][2] - vR[2][1]));
+    dq.z = 2.f * (x * (vR[0][1] + vR[1][0]) - 2.f * y * (vR[0][0] + vR[2][2]) + z * (vR[1][2] + vR[2][1]) + w * (vR[2][0] - vR[0][2]));
+    dq.w = 2.f * (x * (vR[0][2] + vR[2][0]) + y * (vR[1][2] + vR[2][1]) - 2.f * z * (vR[0][0] + vR[1][1]) + w * (vR[0][1] - vR[1][0]));
+    dL_drotations[idx] = dq;
+    dL_dscales[idx] = make_float2(dRS0.x * R[0] + dRS0.y * R[1] + dRS0.z * R[2], dRS1.x * R[3] + dRS1.y * R[4] + dRS1.z * R[5]);
+    float dmean[3] = {dpw.x, dpw.y, dpw.z};
+
+    // ---- SH vjp (backward.cu:20-139) ----
+    if (shs != nullptr) {
+        const float* sh = shs + (size_t)idx * M * 3;
+        const int deg = c.D;
+        const float dox = p.x - __ldg(c.campos), doy = p.y - __ldg(c.campos + 1), doz = p.z - __ldg(c.campos + 2);
+        const float len = sqrtf(dox * dox + doy * doy + doz * doz);
+        const float dx = dox / len, dy = doy / len, dz = doz / len;
+        const uint32_t cl = clamped[idx];
+        float dRGB[3];
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) dRGB[ch] = (cl >> ch) & 1u ? 0.f : dcol[ch];
+        float ddx = 0.f, ddy = 0.f, ddz = 0.f;   // dL/ddir accumulated over channels
+#define SH(k, ch) __ldg(sh + 3 * (k) + (ch))
+#define SETSH(k, wgt) { const float w_ = (wgt); osh[3 * (k)] = w_ * dRGB[0]; osh[3 * (k) + 1] = w_ * dRGB[1]; osh[3 * (k) + 2] = w_ * dRGB[2]; }
+        SETSH(0, kSH_C0);
+        if (deg > 0) {
+            SETSH(1, -kSH_C1 * dy); SETSH(2, kSH_C1 * dz); SETSH(3, -kSH_C1 * dx);
+            const float xx = dx * dx, yy = dy * dy, zz = dz * dz, xy = dx * dy, yz = dy * dz, xz = dx * dz;
+            if (deg > 1) {
+                SETSH(4, kSH_C2[0] * xy); SETSH(5, kSH_C2[1] * yz); SETSH(6, kSH_C2[2] * (2.f * zz - xx - yy));
+                SETSH(7, kSH_C2[3] * xz); SETSH(8, kSH_C2[4] * (xx - yy));
+                if (deg > 2) {
+                    SETSH(9, kSH_C3[0] * dy * (3.f * xx - yy)); SETSH(10, kSH_C3[1] * xy * dz);
+                    SETSH(11, kSH_C3[2] * dy * (4.f * zz - xx - yy)); SETSH(12, kSH_C3[3] * dz * (2.f * zz - 3.f * xx - 3.f * yy));
+                    SETSH(13, kSH_C3[4] * dx * (4.f * zz - xx - yy)); SETSH(14, kSH_C3[5] * dz * (xx - yy));
+                    SETSH(15, kSH_C3[6] * dx * (xx - 3.f * yy));
+                }
+            }
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++) {
+                float gx = -kSH_C1 * SH(3, ch), gy = -kSH_C1 * SH(1, ch), gz = kSH_C1 * SH(2, ch);
+                if (deg > 1) {
+                    gx += kSH_C2[0] * dy * SH(4, ch) + kSH_C2[2] * 2.f * -dx * SH(6, ch) + kSH_C2[3] * dz * SH(7, ch) + kSH_C2[4] * 2.f * dx * SH(8, ch);
+                    gy += kSH_C2[0] * dx * SH(4, ch) + kSH_C2[1] * dz * SH(5, ch) + kSH_C2[2] * 2.f * -dy * SH(6, ch) + kSH_C2[4] * 2.f * -dy * SH(8, ch);
+                    gz += kSH_C2[1] * dy * SH(5, ch) + kSH_C2[2] * 2.f * 2.f * dz * SH(6, ch) + kSH_C2[3] * dx * SH(7, ch);
+                    if (deg > 2) {
+                        gx += kSH_C3[0] * SH(9, ch) * 3.f * 2.f * xy + kSH_C3[1] * SH(10, ch) * yz + kSH_C3[2] * SH(11, ch) * -2.f * xy +
+                              kSH_C3[3] * SH(12, ch) * -3.f * 2.f * xz + kSH_C3[4] * SH(13, ch) * (-3.f * xx + 4.f * zz - yy) +
+                              kSH_C3[5] * SH(14, ch) * 2.f * xz + kSH_C3[6] * SH(15, ch) * 3.f * (xx - yy);
+                        gy += kSH_C3[0] * SH(9, ch) * 3.f * (xx - yy) + kSH_C3[1] * SH(10, ch) * xz +
+                              kSH_C3[2] * SH(11, ch) * (-3.f * yy + 4.f * zz - xx) + kSH_C3[3] * SH(12, ch) * -3.f * 2.f * yz +
+                              kSH_C3[4] * SH(13, ch) * -2.f * xy + kSH_C3[5] * SH(14, ch) * -2.f * yz + kSH_C3[6] * SH(15, ch) * -3.f * 2.f * xy;
+                        gz += kSH_C3[1] * SH(10, ch) * xy + kSH_C3[2] * SH(11, ch) * 4.f * 2.f * yz +
+                              kSH_C3[3] * SH(12, ch) * 3.f * (2.f * zz - xx - yy) + kSH_C3[4] * SH(13, ch) * 4.f * 2.f * xz +
+                              kSH_C3[5] * SH(14, ch) * (xx - yy);
+                    }
+                }
+                ddx += gx * dRGB[ch]; ddy += gy * dRGB[ch]; ddz += gz * dRGB[ch];
+            }
+        }
+        // coefficients above the active degree receive no gradient
+        const int used = (deg + 1) * (deg + 1);
+        for (int k = used; k < M; k++) { osh[3 * k] = 0.f; osh[3 * k + 1] = 0.f; osh[3 * k + 2] = 0.f; }
+#undef SH
+#undef SETSH
+        // through the normalisation of the view direction (auxiliary.h:125-135)
+        const float sum2 = dox * dox + doy * doy + doz * doz;
+        const float inv32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
+        dmean[0] += ((sum2 - dox * dox) * ddx - doy * dox * ddy - doz * dox * ddz) * inv32;
+        dmean[1] += (-dox * doy * ddx + (sum2 - doy * doy) * ddy - doz * doy * ddz) * inv32;
+        dmean[2] += (-dox * doz * ddx - doy * doz * ddy + (sum2 - doz * doz) * ddz) * inv32;
+    }
+    dL_dmeans3D[3 * (size_t)idx] = dmean[0];
+    dL_dmeans3D[3 * (size_t)idx + 1] = dmean[1];
+    dL_dmeans3D[3 * (size_t)idx + 2] = dmean[2];
+}
+
+}  // namespace
+
+cudaError_t launch_surfel_bwd(const BwdArgs& a) {
+    const int nb = a.gl.nblocks;
+    surfel_bwd_kernel<<<nb, 256, 0, a.stream>>>(
+        a.cam, a.means3D, a.shs, (const float2*)a.scales, (const float4*)a.rotations, a.radii,
+        (const float4*)(a.geom + a.gl.surfel_rec), (const uint8_t*)(a.geom + a.gl.clamped),
+        (const float4*)(a.geom + a.gl.sgrad), a.dL_dmeans2D, a.dL_dcolors, a.dL_dopacity, a.dL_dmeans3D,
+        a.dL_dtransMat, a.dL_dsh, (float2*)a.dL_dscales, (float4*)a.dL_drotations);
+    sr_count_launch();
+    return cudaGetLastError();
+}

@@ -1,0 +1,237 @@
+"""render() twin and the caller-side contract of the hot path.
+
+Mirrors (same names, argument meaning, dict keys and error behaviour):
+
+    render(viewpoint_camera, pc, pipe, bg_color, scaling_modifier=1.0, override_color=None)
+                                           gs/gaussian_renderer/__init__.py:21-164
+    depths_to_points / depth_to_normal     gs/utils/point_utils.py:9-37
+    MiniCam / KCamera input contract       gs/scene/cameras.py:59-162
+
+`pc` is duck-typed exactly as the reference uses it: get_xyz (P,3), get_opacity (P,1), get_scaling (P,2),
+get_rotation (P,4), get_features (P,K,3), active_sh_degree, get_covariance().  `pipe` needs
+compute_cov3D_python and depth_ratio.  lab4d's DeformableGaussian.render_view
+(lab4d/nnutils/deformable_gaussian.py:178-190) can call this render() unchanged.
+
+The ~25 small torch ops of the post-processing stay in PyTorch this round (SURVEY.md section 8(f) row N1 is the
+fused version); what is removed here are the reference's per-call host synchronisations other than
+`num_rendered` (tan(FoV) on a CUDA tensor, torch.tensor(...).cuda() + .inverse() per frame,
+point_utils.py:9-18): the per-camera ray table is built once and cached.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import torch
+
+from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer
+
+
+def _tan_half(fov) -> float:
+    if torch.is_tensor(fov):
+        return float(torch.tan(fov * 0.5).item())
+    return math.tan(float(fov) * 0.5)
+
+
+# ---------------------------------------------------------------------------------------------
+# cameras (gs/scene/cameras.py, gs/utils/graphics_utils.py) -- input contract only
+# ---------------------------------------------------------------------------------------------
+def getWorld2View2(R, t, translate=(0.0, 0.0, 0.0), scale=1.0):
+    """gs/utils/graphics_utils.py:38-51 (R is camera-to-world rotation, t world-to-camera translation)."""
+    R = torch.as_tensor(R, dtype=torch.float32)
+    t = torch.as_tensor(t, dtype=torch.float32)
+    Rt = torch.zeros((4, 4), dtype=torch.float32)
+    Rt[:3, :3] = R.T
+    Rt[:3, 3] = t
+    Rt[3, 3] = 1.0
+    C2W = torch.inverse(Rt)
+    C2W[:3, 3] = (C2W[:3, 3] + torch.as_tensor(translate, dtype=torch.float32)) * scale
+    return torch.inverse(C2W).float()
+
+
+def getProjectionMatrix(znear, zfar, fovX, fovY):
+    """gs/utils/graphics_utils.py:53-76"""
+    tanHalfFovY, tanHalfFovX = math.tan(fovY / 2), math.tan(fovX / 2)
+    top, right = tanHalfFovY * znear, tanHalfFovX * znear
+    bottom, left = -top, -right
+    P = torch.zeros(4, 4)
+    P[0, 0] = 2.0 * znear / (right - left)
+    P[1, 1] = 2.0 * znear / (top - bottom)
+    P[0, 2] = (right + left) / (right - left)
+    P[1, 2] = (top + bottom) / (top - bottom)
+    P[3, 2] = 1.0
+    P[2, 2] = zfar / (zfar - znear)
+    P[2, 3] = -(zfar * znear) / (zfar - znear)
+    return P
+
+
+@dataclass
+class MiniCam:
+    """gs/scene/cameras.py:59-71 -- everything render() reads from a camera."""
+    image_width: int
+    image_height: int
+    FoVy: float
+    FoVx: float
+    znear: float
+    zfar: float
+    world_view_transform: torch.Tensor   # (4,4) = W2C transposed (row-vector convention)
+    full_proj_transform: torch.Tensor    # (4,4)
+    camera_center: torch.Tensor = None
+
+    def __post_init__(self):
+        if self.camera_center is None:
+            self.camera_center = torch.inverse(self.world_view_transform)[3][:3]
+
+
+def make_camera(width, height, fovx, fovy, R=None, T=None, device="cuda", znear=0.01, zfar=100.0) -> MiniCam:
+    """Camera from a camera-to-world rotation R (3,3) and world-to-camera translation T (3,), as
+    gs/scene/cameras.py:17-57 builds it.  R=None,T=None gives the Stage-3 identity camera (cameras.py:84-85)."""
+    R = torch.eye(3) if R is None else torch.as_tensor(R, dtype=torch.float32)
+    T = torch.zeros(3) if T is None else torch.as_tensor(T, dtype=torch.float32)
+    wvt = getWorld2View2(R, T).transpose(0, 1)
+    proj = getProjectionMatrix(znear, zfar, fovx, fovy).transpose(0, 1)
+    full = wvt.unsqueeze(0).bmm(proj.unsqueeze(0)).squeeze(0)
+    center = torch.inverse(wvt)[3, :3]
+    return MiniCam(int(width), int(height), float(fovy), float(fovx), znear, zfar, wvt.to(device).contiguous(),
+                   full.to(device).contiguous(), center.to(device).contiguous())
+
+
+# ---------------------------------------------------------------------------------------------
+# gs/utils/point_utils.py
+# ---------------------------------------------------------------------------------------------
+_ray_cache: dict = {}
+
+
+def _rays(view, device):
+    """rays_d (H*W,3) and rays_o (3,) of depths_to_points (point_utils.py:9-21), cached per camera so the
+    per-frame torch.tensor(...).cuda(), .inverse() and math.tan(cuda tensor) host syncs disappear."""
+    W, H = int(view.image_width), int(view.image_height)
+    wvt = view.world_view_transform
+    key = (W, H, _tan_half(view.FoVx), _tan_half(view.FoVy), wvt.data_ptr(), wvt._version, str(device))
+    hit = _ray_cache.get(key)
+    if hit is not None:
+        return hit
+    c2w = (wvt.T).inverse()
+    fx = W / (2 * _tan_half(view.FoVx))
+    fy = H / (2 * _tan_half(view.FoVy))
+    intrins = torch.tensor([[fx, 0., W / 2.], [0., fy, H / 2.], [0., 0., 1.0]], dtype=torch.float32, device=device)
+    grid_x, grid_y = torch.meshgrid(torch.arange(W, device=device).float(), torch.arange(H, device=device).float(),
+                                    indexing='xy')
+    points = torch.stack([grid_x, grid_y, torch.ones_like(grid_x)], dim=-1).reshape(-1, 3)
+    rays_d = points @ intrins.inverse().T @ c2w[:3, :3].T
+    rays_o = c2w[:3, 3]
+    if len(_ray_cache) > 64:
+        _ray_cache.clear()
+    _ray_cache[key] = (rays_d, rays_o)
+    return rays_d, rays_o
+
+
+def depths_to_points(view, depthmap):
+    rays_d, rays_o = _rays(view, depthmap.device)
+    return depthmap.reshape(-1, 1) * rays_d + rays_o
+
+
+def depth_to_normal(view, depth):
+    """view: camera; depth: (1,H,W).  Returns (H,W,3) pseudo surface normals (point_utils.py:23-37)."""
+    points = depths_to_points(view, depth).reshape(*depth.shape[1:], 3)
+    output = torch.zeros_like(points)
+    dx = points[2:, 1:-1] - points[:-2, 1:-1]
+    dy = points[1:-1, 2:] - points[1:-1, :-2]
+    normal_map = torch.nn.functional.normalize(torch.cross(dx, dy, dim=-1), dim=-1)
+    output[1:-1, 1:-1, :] = normal_map
+    return output
+
+
+# ---------------------------------------------------------------------------------------------
+# gs/gaussian_renderer/__init__.py:21-164
+# ---------------------------------------------------------------------------------------------
+def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=1.0, override_color=None):
+    """Render the scene.  Background tensor (bg_color) must be on GPU!"""
+    xyz = pc.get_xyz
+    screenspace_points = torch.zeros_like(xyz, dtype=xyz.dtype, requires_grad=True, device=xyz.device) + 0
+    try:
+        screenspace_points.retain_grad()
+    except Exception:
+        pass
+
+    tanfovx = _tan_half(viewpoint_camera.FoVx)
+    tanfovy = _tan_half(viewpoint_camera.FoVy)
+    raster_settings = GaussianRasterizationSettings(
+        image_height=int(viewpoint_camera.image_height),
+        image_width=int(viewpoint_camera.image_width),
+        tanfovx=tanfovx,
+        tanfovy=tanfovy,
+        bg=bg_color,
+        scale_modifier=scaling_modifier,
+        viewmatrix=viewpoint_camera.world_view_transform,
+        projmatrix=viewpoint_camera.full_proj_transform,
+        sh_degree=pc.active_sh_degree,
+        campos=viewpoint_camera.camera_center,
+        prefiltered=False,
+        debug=False,
+    )
+    rasterizer = GaussianRasterizer(raster_settings=raster_settings)
+    means3D = xyz
+    means2D = screenspace_points
+    opacity = pc.get_opacity
+
+    scales = None
+    rotations = None
+    cov3D_precomp = None
+    if pipe.compute_cov3D_python:
+        cov3D_precomp = pc.get_covariance(scaling_modifier)
+    else:
+        scales = pc.get_scaling
+        rotations = pc.get_rotation
+
+    # the reference always passes SHs *and* override_color; with a non-None override_color the rasterizer
+    # raises (gaussian_renderer/__init__.py:91-92 vs RAST/.../__init__.py:192-193) -- preserved.
+    shs = pc.get_features
+    colors_precomp = override_color
+
+    try:
+        means3D.retain_grad()
+    except Exception:
+        pass
+    rendered_image, radii, allmap = rasterizer(
+        means3D=means3D, means2D=means2D, shs=shs, colors_precomp=colors_precomp, opacities=opacity,
+        scales=scales, rotations=rotations, cov3D_precomp=cov3D_precomp)
+
+    rets = {"render": rendered_image,
+            "viewspace_points": means2D,
+            "visibility_filter": radii > 0,
+            "radii": radii}
+
+    render_alpha = allmap[1:2]
+    render_normal = allmap[2:5]
+    render_normal = (render_normal.permute(1, 2, 0) @ (viewpoint_camera.world_view_transform[:3, :3].T)).permute(2, 0, 1)
+    render_depth_median = allmap[5:6]
+    render_depth_median = torch.nan_to_num(render_depth_median, 0, 0)
+    render_depth_expected = allmap[0:1]
+    render_depth_expected = (render_depth_expected / render_alpha)
+    render_depth_expected = torch.nan_to_num(render_depth_expected, 0, 0)
+    render_dist = allmap[6:7]
+    surf_depth = render_depth_expected * (1 - pipe.depth_ratio) + (pipe.depth_ratio) * render_depth_median
+    surf_normal = depth_to_normal(viewpoint_camera, surf_depth)
+    surf_normal = surf_normal.permute(2, 0, 1)
+    surf_normal = surf_normal * (render_alpha).detach()
+
+    rets.update({
+        'acc': render_alpha,
+        'rend_normal': render_normal,
+        'rend_dist': render_dist,
+        'surf_depth': torch.cat([surf_depth] * 3, 0),
+        'render_depth_median': torch.cat([render_depth_median] * 3, 0),
+        'render_depth_expected': torch.cat([render_depth_expected] * 3, 0),
+        'surf_normal': surf_normal,
+    })
+    return rets
+
+
+@dataclass
+class PipelineParams:
+    """gs/arguments/__init__.py PipelineParams, as instantiated at deformable_gaussian.py:158-160."""
+    convert_SHs_python: bool = False
+    compute_cov3D_python: bool = False
+    depth_ratio: float = 0.0
+    debug: bool = False

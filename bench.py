@@ -1,0 +1,417 @@
+#!/usr/bin/env python
+"""bench.py -- surfel-rasterizer forward+backward frames/s at 512x512 / 300 K surfels (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A STEP = one pass of the hot path over one batch: every rank rasterizes `--frames-per-step` frames (forward +
+backward, each frame a different camera), accumulates the surfel gradients, and -- for N > 1 -- joins ONE NCCL
+all-reduce of the flat gradient buffer (frames are the shard axis; weak scaling: per-GPU work is fixed).
+
+One JSON line (rank 0):
+  value       frames/s over all ranks, inputs resident in HBM, C-ABI calls, device-event timed (max over ranks)
+  e2e         frames/s through the public API render() -> loss -> backward -> (all-reduce) -> Adam step, with each
+              step's camera block + target images copied from pinned host memory and the loss read back
+  roofline    the dominant kernel: algorithmic bytes / its CUDA-event time (sr_set_profiling) vs MEASURED_PEAKS.json
+  cpu_baseline  the oracle (C restatement, OpenMP) fwd+bwd on host cores on a bounded sample of the same frames
+  reference_cuda  (ours arm, N=1) the unmodified reference extension timed in the same run, same frames
+
+--impl reference runs the UNMODIFIED reference extension (oracle/_ref/_C.so, its own CUDA path) through the same
+harness; if the .so is missing it falls back to the CPU oracle port and says so.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from vidu4d_b200 import distributed as D  # noqa: E402
+from vidu4d_b200.synthetic import SurfelCloud, object_scene, orbit_view, projection_matrix  # noqa: E402
+
+NVIEWS = 64
+TAN = 0.5
+L2_MB = 126
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--surfels", type=int, default=300_000)
+    ap.add_argument("--res", type=int, default=512)
+    ap.add_argument("--frames-per-step", type=int, default=8)
+    ap.add_argument("--opacity", default="trained", choices=["trained", "init"])
+    ap.add_argument("--cpu-frames", type=int, default=2, help="frames of the cpu_baseline sample (0 = skip)")
+    ap.add_argument("--no-ref-cuda", action="store_true", help="skip timing the reference extension in the ours arm")
+    ap.add_argument("--ref-device", default="cuda", choices=["cuda", "cpu"])
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_views(device):
+    vms, cps, pms = [], [], []
+    P = projection_matrix(TAN, TAN).astype(np.float64)
+    for f in range(NVIEWS):
+        R, t = orbit_view(f, NVIEWS)
+        W2C = np.eye(4); W2C[:3, :3] = R; W2C[:3, 3] = t
+        vm = W2C.T
+        vms.append(vm.astype(np.float32)); pms.append((vm @ P).astype(np.float32)); cps.append((-R.T @ t).astype(np.float32))
+    return np.stack(vms), np.stack(pms), np.stack(cps)
+
+
+def sync_all(world):
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(ms: float, world: int, device) -> float:
+    if world == 1:
+        return ms
+    t = torch.tensor([ms], dtype=torch.float64, device=device)
+    torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    return float(t.item())
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    rank, world, local_rank = D.env_rank_world()
+    if args.impl == "reference" and (args.ref_device == "cpu" or not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "_C.so"))):
+        return reference_cpu_arm(args, rank, world)
+    assert torch.cuda.is_available(), "bench.py needs a GPU (the CPU oracle is only the baseline leg)"
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    D.init_distributed("nccl", device)
+    F, K, Wm, RES, P = args.frames_per_step, args.steps, max(args.warmup, 3), args.res, args.surfels
+
+    from vidu4d_b200 import _capi, rasterizer as RZ, renderer as RN
+    if args.impl == "reference":
+        from oracle import ref_ext
+        ref_ext.load()
+        RN.GaussianRasterizer = ref_ext.RefGaussianRasterizer        # same render() glue, reference rasterizer under it
+    else:
+        _capi.load()   # fail loudly if the CUDA library is missing
+
+    scene = object_scene(P, seed=0, opacity=args.opacity, center=(0.0, 0.0, 0.0))
+    cloud = SurfelCloud(scene, device)
+    vms_h, pms_h, cps_h = build_views(device)
+    vms = torch.from_numpy(vms_h).to(device); pms = torch.from_numpy(pms_h).to(device); cps = torch.from_numpy(cps_h).to(device)
+    bg = torch.zeros(3, device=device)
+    g = torch.Generator(device=device).manual_seed(1234)
+    dLc = torch.randn((3, RES, RES), device=device, generator=g)
+    dLo = torch.randn((8, RES, RES), device=device, generator=g) * 0.1
+    flush = torch.empty((256 << 20,), dtype=torch.uint8, device=device)     # > L2 (126 MB)
+    e = torch.empty((0,), device=device)
+
+    with torch.no_grad():
+        t_in = dict(means3D=cloud.get_xyz.detach().contiguous(), opac=cloud.get_opacity.detach().contiguous(),
+                    scales=cloud.get_scaling.detach().contiguous(), rots=cloud.get_rotation.detach().contiguous(),
+                    shs=cloud.get_features.detach().contiguous())
+    acc = [torch.zeros_like(t_in[k]) for k in ("means3D", "shs", "opac", "scales", "rots")]
+    acc_flat_bytes = sum(a.numel() for a in acc) * 4
+
+    def view_of(step, f):
+        return (step * world * F + rank * F + f) % NVIEWS
+
+    # ---------------- device-resident arm: C-ABI level (or the reference's pybind _C) ----------------
+    if args.impl == "ours":
+        C = RZ._C
+        RZ.set_sync_mode(False)
+
+        def frame_dev(v):
+            o = C.rasterize_gaussians(bg, t_in["means3D"], e, t_in["opac"], t_in["scales"], t_in["rots"], 1.0, e, vms[v],
+                                      pms[v], TAN, TAN, RES, RES, t_in["shs"], 3, cps[v], False, False)
+            return o, C.rasterize_gaussians_backward(bg, t_in["means3D"], o[3], e, t_in["scales"], t_in["rots"], 1.0, e,
+                                                     vms[v], pms[v], TAN, TAN, dLc, dLo, t_in["shs"], 3, cps[v], o[4],
+                                                     o[0], o[5], o[6], False)
+    else:
+        from oracle import ref_ext
+        Cr = ref_ext.load()
+
+        def frame_dev(v):
+            o = Cr.rasterize_gaussians(bg, t_in["means3D"], e, t_in["opac"], t_in["scales"], t_in["rots"], 1.0, e, vms[v],
+                                       pms[v], TAN, TAN, RES, RES, t_in["shs"], 3, cps[v], False, False)
+            return o, Cr.rasterize_gaussians_backward(bg, t_in["means3D"], o[3], e, t_in["scales"], t_in["rots"], 1.0, e,
+                                                      vms[v], pms[v], TAN, TAN, dLc, dLo, t_in["shs"], 3, cps[v], o[4],
+                                                      o[0], o[5], o[6], False)
+
+    flat_acc = torch.zeros((acc_flat_bytes // 4,), device=device)
+
+    def step_dev(step):
+        R_last = 0
+        for f in range(F):
+            o, gr = frame_dev(view_of(step, f))
+            # gr = (dmeans2D, dcolors, dopacity, dmeans3D, dtransMat, dsh, dscales, drots)
+            acc[0].add_(gr[3]); acc[1].add_(gr[5]); acc[2].add_(gr[2]); acc[3].add_(gr[6]); acc[4].add_(gr[7])
+            R_last = o[0]
+        if world > 1:
+            torch.cat([a.reshape(-1) for a in acc], out=flat_acc)
+            torch.distributed.all_reduce(flat_acc)
+        if args.impl == "ours":
+            RZ.check_overflow()     # the step's only host<->device synchronisation
+        return R_last
+
+    def timed(step_fn, nsteps, nwarm):
+        for s in range(nwarm):
+            step_fn(s)
+        sync_all(world)
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(nsteps)]
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(nsteps)]
+        t0 = time.perf_counter()
+        for s in range(nsteps):
+            flush.fill_(s & 255)                      # L2 flush between timed iterations (not timed)
+            starts[s].record()
+            step_fn(nwarm + s)
+            ends[s].record()
+        sync_all(world)
+        wall = (time.perf_counter() - t0) * 1e3
+        per = [a.elapsed_time(b) for a, b in zip(starts, ends)]
+        return sum(per), per, wall
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = _capi.launch_count() if args.impl == "ours" else 0
+    total_ms, per_ms, wall_ms = timed(step_dev, K, Wm)
+    launches = (_capi.launch_count() - launches0) if args.impl == "ours" else None
+    total_ms = max_over_ranks(total_ms, world, device)
+    frames = K * F * world
+    value = frames / (total_ms * 1e-3)
+
+    # R (instances) of a representative frame, for the algorithmic-byte figures
+    if args.impl == "ours":
+        RZ.set_sync_mode(True)
+        o_probe = RZ._C.rasterize_gaussians(bg, t_in["means3D"], e, t_in["opac"], t_in["scales"], t_in["rots"], 1.0, e, vms[0],
+                                            pms[0], TAN, TAN, RES, RES, t_in["shs"], 3, cps[0], False, False)
+        R_inst = int(o_probe[0])
+        RZ.set_sync_mode(False)
+    else:
+        R_inst = int(frame_dev(0)[0][0])
+
+    # ---------------- e2e arm: public API with host buffers ----------------
+    from vidu4d_b200.renderer import MiniCam, PipelineParams, render
+    pipe = PipelineParams()
+    params = cloud.flat_params()
+    fg = D.FlatGrads(params)
+    opt = torch.optim.Adam(params, lr=1e-7, fused=True)
+    targets_h = torch.rand((F, 3, RES, RES), generator=torch.Generator().manual_seed(5)).pin_memory()
+    cam_h = torch.empty((F, 2, 4, 4)).pin_memory()       # viewmatrix, full_proj per frame
+    cps_hh = torch.empty((F, 3)).pin_memory()
+    loss_h = torch.empty((1,)).pin_memory()
+    h2d = targets_h.numel() * 4 + cam_h.numel() * 4 + cps_hh.numel() * 4
+    fov = 2.0 * float(np.arctan(TAN))
+
+    def step_e2e(step):
+        for f in range(F):
+            v = view_of(step, f)
+            cam_h[f, 0] = torch.from_numpy(vms_h[v]); cam_h[f, 1] = torch.from_numpy(pms_h[v]); cps_hh[f] = torch.from_numpy(cps_h[v])
+        tg = targets_h.to(device, non_blocking=True); cam = cam_h.to(device, non_blocking=True); cp = cps_hh.to(device, non_blocking=True)
+        fg.zero_()
+        tot = torch.zeros((), device=device)
+        for f in range(F):
+            view = MiniCam(RES, RES, fov, fov, 0.01, 100.0, cam[f, 0], cam[f, 1], cp[f])
+            out = render(view, cloud, pipe, bg)
+            loss = (out["render"] - tg[f]).abs().mean() + 0.05 * (1.0 - (out["rend_normal"] * out["surf_normal"]).sum(0)).mean() \
+                + 0.01 * out["rend_dist"].mean()
+            loss.backward()
+            tot += loss.detach()
+        fg.allreduce_(average_over=F * world)
+        opt.step()
+        loss_h.copy_(tot.reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        if args.impl == "ours":
+            RZ.check_overflow()
+        return float(loss_h[0])
+
+    e2e_total, _, _ = timed(step_e2e, K, Wm)
+    e2e_total = max_over_ranks(e2e_total, world, device)
+    e2e_value = frames / (e2e_total * 1e-3)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---------------- per-kernel profile + roofline (ours only) ----------------
+    roofline, kernels = None, None
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json (measured)" if peaks else "B200_PROFILING.md fallback 6650 GB/s"
+    N = RES * RES
+    if args.impl == "ours" and rank == 0:
+        _capi.get_profile()
+        _capi.set_profiling(True)
+        nprof = 6
+        for f in range(nprof):
+            frame_dev(f % NVIEWS)
+        prof = _capi.get_profile()
+        _capi.set_profiling(False)
+        RZ.check_overflow()
+        Vv = P
+        alg = {   # algorithmic bytes per launch (DESIGN.md "algorithmic bytes")
+            "preprocess_fwd": P * (40 + 12 * 16) + Vv * 93,
+            "scan_block_sums": (P // 256) * 8, "emit_keys": P * 20 + R_inst * 12,
+            "sort_histogram": R_inst * 8, "sort_plan": 6 * 256 * 8, "onesweep_passes": R_inst * 24 * 6,
+            "ranges_gather": R_inst * (12 + 80 + 80), "composite_fwd": R_inst * 80 + N * 64,
+            "composite_bwd": R_inst * 80 + N * 64 + Vv * 72, "surfel_bwd": Vv * (343 + 240),
+        }
+        kernels = {}
+        for k, v in prof.items():
+            ms = v["ms"] / max(v["count"], 1)
+            kernels[k] = {"ms": round(ms, 5), "alg_MB": round(alg.get(k, 0) / 1e6, 2),
+                          "GBps": round(alg.get(k, 0) / 1e9 / (ms * 1e-3), 1) if ms > 0 else None}
+        dom = max(kernels, key=lambda k: kernels[k]["ms"])
+        ach = kernels[dom]["GBps"]
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": round(ach / hbm_peak, 5), "traffic": None, "peak_source": peak_src,
+                    "note": "the composite kernels are FP32-issue/shared-memory bound by construction (SURVEY 8d); "
+                            "algorithmic HBM bytes are small, see profiles/ for ncu pipe utilisation",
+                    "frame_alg_MB": round((1002 * P + 324 * R_inst + 128 * N) / 1e6, 1),
+                    "frame_GBps": round((1002 * P + 324 * R_inst + 128 * N) / 1e9 / (total_ms * 1e-3 / (K * F)), 1)}
+
+    # ---------------- reference CUDA extension in the same run (ours arm, rank 0, N=1) ----------------
+    reference_cuda = None
+    if args.impl == "ours" and world == 1 and not args.no_ref_cuda and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "_C.so")):
+        try:
+            from oracle import ref_ext
+            Cr = ref_ext.load()
+
+            def ref_step(step):
+                for f in range(F):
+                    v = view_of(step, f)
+                    o = Cr.rasterize_gaussians(bg, t_in["means3D"], e, t_in["opac"], t_in["scales"], t_in["rots"], 1.0, e, vms[v],
+                                               pms[v], TAN, TAN, RES, RES, t_in["shs"], 3, cps[v], False, False)
+                    gr = Cr.rasterize_gaussians_backward(bg, t_in["means3D"], o[3], e, t_in["scales"], t_in["rots"], 1.0, e,
+                                                         vms[v], pms[v], TAN, TAN, dLc, dLo, t_in["shs"], 3, cps[v], o[4],
+                                                         o[0], o[5], o[6], False)
+                    acc[0].add_(gr[3]); acc[1].add_(gr[5]); acc[2].add_(gr[2]); acc[3].add_(gr[6]); acc[4].add_(gr[7])
+            rt, _, _ = timed(ref_step, max(3, K // 2), 3)
+            reference_cuda = {"value": round(max(3, K // 2) * F / (rt * 1e-3), 2), "unit": "frames/s",
+                              "what": "unmodified reference extension (oracle/_ref/_C.so, sm_100a), same frames, device-resident"}
+        except Exception as ex:  # pragma: no cover
+            reference_cuda = {"unavailable": repr(ex)}
+
+    # ---------------- CPU baseline (oracle port) ----------------
+    cpu_baseline = None
+    if rank == 0 and world == 1 and args.cpu_frames > 0:
+        cpu_baseline = cpu_oracle_fps(scene, vms_h, pms_h, cps_h, RES, args.cpu_frames, dLc.cpu().numpy(), dLo.cpu().numpy())
+
+    if rank == 0:
+        line = {
+            "metric": "raster fwd+bwd frames/sec @512^2, 300K surfels", "value": round(value, 2), "unit": "frames/s",
+            "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": round(total_ms / K, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": args.impl,
+            "config": {"workload": f"HL: {P} surfels (seeded noisy sphere, SH deg 3, opacity={args.opacity}), {RES}x{RES}, "
+                                   f"{F} frames/step/GPU on orbiting cameras, colour+depth+normal+distortion fwd+bwd",
+                       "surfels": P, "resolution": RES, "frames_per_step_per_gpu": F, "instances_per_frame": R_inst,
+                       "parallelism": f"frames sharded over {world} GPU(s), 1 NCCL all-reduce of {acc_flat_bytes >> 20} MiB/step" if world > 1 else "1 GPU",
+                       "l2": f"explicit flush (256 MiB write) between timed steps; per-step working set also exceeds the {L2_MB} MB L2"},
+            "e2e": {"value": round(e2e_value, 2), "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
+                    "what": "render() -> L1+normal+distortion loss -> backward -> (all-reduce) -> fused Adam; per step the "
+                            "cameras + target images come from pinned host memory, the loss is read back"},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels_ms": kernels,
+            "cpu_baseline": cpu_baseline, "reference_cuda": reference_cuda, "wall_ms_timed_region": round(wall_ms, 1),
+        }
+        if args.impl == "reference":
+            line["cpu_baseline"] = {"value": line["value"], "unit": "frames/s", "cores": 0, "kind": "reference",
+                                    "sample": "the reference's only implementation of this path is CUDA: this arm runs "
+                                              "oracle/_ref/_C.so on the GPU (no CPU cores involved); see --ref-device cpu for the oracle port"}
+            line["e2e"]["h2d_bytes_per_step"] = int(h2d)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+    return 0
+
+
+def cpu_oracle_fps(scene, vms_h, pms_h, cps_h, RES, nframes, dLc, dLo):
+    from oracle import surfel_oracle as so
+    so.lib()
+    t0 = time.perf_counter()
+    for f in range(nframes):
+        st = so.forward(scene.means3D, scene.opacities, scene.scales, scene.rotations, shs=scene.shs, sh_degree=3, W=RES, H=RES,
+                        tanfovx=TAN, tanfovy=TAN, bg=(0, 0, 0), viewmatrix=vms_h[f], projmatrix=pms_h[f], campos=cps_h[f])
+        so.backward(st, dLc, dLo)
+    dt = time.perf_counter() - t0
+    return {"value": round(nframes / dt, 4), "unit": "frames/s", "cores": so.num_threads(), "kind": "port",
+            "sample": f"{nframes} full frames of the same workload (fwd+bwd), oracle/surfel_oracle.c with OpenMP"}
+
+
+def reference_cpu_arm(args, rank, world):
+    """--impl reference when oracle/_ref is absent (or --ref-device cpu): the oracle port on the host cores."""
+    if rank != 0:
+        return 0
+    scene = object_scene(args.surfels, seed=0, opacity=args.opacity, center=(0.0, 0.0, 0.0))
+    vms_h, pms_h, cps_h = build_views(None)
+    rng = np.random.default_rng(0)
+    dLc = rng.normal(size=(3, args.res, args.res)).astype(np.float32)
+    dLo = (0.1 * rng.normal(size=(8, args.res, args.res))).astype(np.float32)
+    n = max(1, min(args.steps, 4))
+    cb = cpu_oracle_fps(scene, vms_h, pms_h, cps_h, args.res, n, dLc, dLo)
+    line = {"metric": "raster fwd+bwd frames/sec @512^2, 300K surfels", "value": cb["value"], "unit": "frames/s",
+            "n_gpus": args.gpus, "steps": n, "warmup": 0, "ms_per_step": round(1e3 / cb["value"], 2), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": f"HL: {args.surfels} surfels, {args.res}x{args.res}; one frame per step on the host cores"},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

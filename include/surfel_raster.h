@@ -143,6 +143,9 @@ SR_API int sr_abi_version(void);
 SR_API const char* sr_last_error(void);
 /* number of kernel launches issued by this library since load (bench.py's `gpu_launches`) */
 SR_API uint64_t sr_launch_count(void);
+/* per-kernel device timing for bench.py's roofline: CUDA events on the launching stream around every kernel */
+SR_API void sr_set_profiling(int on);
+SR_API const char* sr_get_profile(void);   /* JSON {"kernel": {"ms": total, "count": n}}; synchronises */
 
 #ifdef __cplusplus
 }

@@ -119,3 +119,60 @@ def decode_image(imgBuffer, W, H):
 
 def to_np(x):
     return x.detach().cpu().numpy() if torch.is_tensor(x) else np.asarray(x)
+
+
+# ---------------------------------------------------------------------------------------------
+# autograd wrapper over the reference `_C` (for bench.py --impl reference and the API-level parity test):
+# same forward/backward contract as RAST/diff_surfel_rasterization/__init__.py:44-156,172-222.
+# ---------------------------------------------------------------------------------------------
+class _RefRasterize(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs):
+        C = load()
+        out = C.rasterize_gaussians(rs.bg, means3D, colors_precomp, opacities, scales, rotations, rs.scale_modifier,
+                                    cov3Ds_precomp, rs.viewmatrix, rs.projmatrix, float(rs.tanfovx), float(rs.tanfovy),
+                                    rs.image_height, rs.image_width, sh, rs.sh_degree, rs.campos, rs.prefiltered, rs.debug)
+        num_rendered, color, depth, radii, geomBuffer, binningBuffer, imgBuffer = out
+        ctx.rs = rs
+        ctx.num_rendered = num_rendered
+        ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geomBuffer,
+                              binningBuffer, imgBuffer)
+        ctx.mark_non_differentiable(radii)
+        return color, radii, depth
+
+    @staticmethod
+    def backward(ctx, grad_out_color, grad_radii, grad_depth):
+        C = load()
+        rs = ctx.rs
+        colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geomBuffer, binningBuffer, imgBuffer = ctx.saved_tensors
+        if grad_out_color is None:
+            grad_out_color = torch.zeros((3, rs.image_height, rs.image_width), device=means3D.device)
+        if grad_depth is None:
+            grad_depth = torch.zeros((8, rs.image_height, rs.image_width), device=means3D.device)
+        g = C.rasterize_gaussians_backward(rs.bg, means3D, radii, colors_precomp, scales, rotations, rs.scale_modifier,
+                                           cov3Ds_precomp, rs.viewmatrix, rs.projmatrix, float(rs.tanfovx),
+                                           float(rs.tanfovy), grad_out_color.contiguous(), grad_depth.contiguous(), sh,
+                                           rs.sh_degree, rs.campos, geomBuffer, ctx.num_rendered, binningBuffer,
+                                           imgBuffer, rs.debug)
+        gm2, gcol, gop, gm3, gcov, gsh, gsc, grot = g
+        return (gm3, gm2, gsh if sh.numel() else None, gcol if colors_precomp.numel() else None, gop, gsc, grot,
+                None, None)
+
+
+class RefGaussianRasterizer(torch.nn.Module):
+    """Drop-in for GaussianRasterizer backed by the reference extension (bench reference arm / parity tests)."""
+
+    def __init__(self, raster_settings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                cov3D_precomp=None):
+        if (shs is None) == (colors_precomp is None):
+            raise Exception('Please provide excatly one of either SHs or precomputed colors!')
+        dev = means3D.device
+        e = lambda: torch.empty((0,), dtype=torch.float32, device=dev)  # noqa: E731
+        return _RefRasterize.apply(means3D, means2D, shs if shs is not None else e(),
+                                   colors_precomp if colors_precomp is not None else e(), opacities,
+                                   scales if scales is not None else e(), rotations if rotations is not None else e(),
+                                   cov3D_precomp if cov3D_precomp is not None else e(), self.raster_settings)

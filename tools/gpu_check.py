@@ -57,7 +57,7 @@ def run_case(name, P, W, H, seed, rigid=False, opacity="trained", colors_precomp
         res["keys_mismatch"] = int((d["keys"] != rb["keys"]).sum().item())
         res["point_list_mismatch"] = int((d["point_list"] != rb["point_list"]).sum().item())
     res["ranges_mismatch"] = int((d["ranges"] != ri["ranges"]).sum().item())
-    res["n_contrib_mismatch"] = int((d["n_contrib"] != ri["n_contrib"]).sum().item())
+    res["n_contrib_last_mismatch"] = int((d["n_contrib"][0] != ri["n_contrib"][0]).sum().item())
     res["final_T_bits_mismatch"] = int((d["final_T"].view(torch.int32) != ri["final_T"].view(torch.int32)).sum().item())
     res["color_bits_mismatch"] = int((color.view(torch.int32) != fw["color"].view(torch.int32)).sum().item())
     res["color_maxabs"] = float((color - fw["color"]).abs().max().item())

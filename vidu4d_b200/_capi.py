@@ -18,6 +18,7 @@ SR_STATUS_PREFILTER = 4
 SYMBOLS = (
     "sr_geom_bytes", "sr_image_bytes", "sr_binning_bytes", "sr_forward", "sr_backward",
     "sr_mark_visible", "sr_debug_view", "sr_abi_version", "sr_last_error", "sr_launch_count",
+    "sr_set_profiling", "sr_get_profile",
 )
 
 
@@ -78,6 +79,9 @@ def load():
     lib.sr_mark_visible.argtypes = [i32, f32p, f32p, f32p, vp, vp]
     lib.sr_debug_view.restype = C.c_int
     lib.sr_debug_view.argtypes = [i32, i32, i32, i64, C.POINTER(SrDebugLayout)]
+    lib.sr_set_profiling.restype = None
+    lib.sr_set_profiling.argtypes = [C.c_int]
+    lib.sr_get_profile.restype = C.c_char_p
     if lib.sr_abi_version() != ABI_VERSION:
         raise SurfelRasterError(f"ABI mismatch: library {lib.sr_abi_version()} != binding {ABI_VERSION}")
     _lib = lib
@@ -92,3 +96,13 @@ def check(rc: int, what: str):
 
 def launch_count() -> int:
     return int(load().sr_launch_count())
+
+
+def set_profiling(on: bool):
+    load().sr_set_profiling(1 if on else 0)
+
+
+def get_profile() -> dict:
+    """{"kernel": {"ms": total, "count": n}} since the previous call (synchronises the device)."""
+    import json
+    return json.loads(load().sr_get_profile().decode())

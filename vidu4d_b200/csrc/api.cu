@@ -4,6 +4,10 @@
 //   GeometryState/ImageState/BinningState::fromChunk, required<T>   rasterizer_impl.cu:155-194, rasterizer_impl.h:66-72
 // No torch types; no host<->device synchronisation on the forward/backward path (debug mode excepted).
 #include <atomic>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -69,11 +73,49 @@ int check_frame(const sr_frame* f) {
 
 void sr_count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
+namespace {
+std::atomic<bool> g_profiling{false};
+std::mutex g_prof_mu;
+struct ProfRec { const char* name; cudaEvent_t e0, e1; };
+std::vector<ProfRec> g_prof;
+std::string g_prof_json;
+}  // namespace
+bool sr_profiling_on() { return g_profiling.load(std::memory_order_relaxed); }
+void sr_profile_push(const char* name, cudaEvent_t e0, cudaEvent_t e1) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof.push_back({name, e0, e1});
+}
+
 extern "C" {
 
 int sr_abi_version(void) { return SR_ABI_VERSION; }
 const char* sr_last_error(void) { return g_err; }
 uint64_t sr_launch_count(void) { return g_launches.load(); }
+
+void sr_set_profiling(int on) { g_profiling.store(on != 0); }
+
+// Synchronises the device, then returns {"kernel": {"ms": total, "count": n}, ...} for everything recorded
+// since the previous call.  The returned pointer stays valid until the next call.
+const char* sr_get_profile(void) {
+    cudaDeviceSynchronize();
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    std::map<std::string, std::pair<double, int>> acc;
+    for (auto& r : g_prof) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) { acc[r.name].first += ms; acc[r.name].second += 1; }
+        cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+    }
+    g_prof.clear();
+    g_prof_json = "{";
+    bool first = true;
+    for (auto& kv : acc) {
+        char buf[256];
+        snprintf(buf, sizeof(buf), "%s\"%s\": {\"ms\": %.6f, \"count\": %d}", first ? "" : ", ", kv.first.c_str(), kv.second.first, kv.second.second);
+        g_prof_json += buf; first = false;
+    }
+    g_prof_json += "}";
+    return g_prof_json.c_str();
+}
 
 size_t sr_geom_bytes(int32_t P) { return geom_layout(P).total; }
 size_t sr_image_bytes(int32_t width, int32_t height) { return image_layout(width, height).total; }

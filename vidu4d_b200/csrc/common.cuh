@@ -23,7 +23,7 @@
 //  18     surfel record: packed conservative pixel bbox x (lo16 = x0, hi16 = x1)
 //         instance record: surfel id
 //  19     surfel record: packed conservative pixel bbox y
-//         instance record: tile-local cull rect  lx0 | lx1<<4 | ly0<<8 | ly1<<12 | valid<<16
+//         instance record: tile-local cull rect  lx0 | lx1<<4 | ly0<<8 | ly1<<12 | valid<<16 | rho_cut(1/1024)<<17
 #define SR_R_T 0
 #define SR_R_XY 9
 #define SR_R_OPAC 11
@@ -93,7 +93,7 @@ static inline __host__ __device__ ImageLayout image_layout(int W, int H) {
     L.final_T = o;   o = sr_align_up(o + 3 * N * 4);
     L.n_contrib = o; o = sr_align_up(o + 2 * N * 4);
     L.ranges = o;    o = sr_align_up(o + (size_t)L.tiles * 8);
-    L.tile_last = o; o = sr_align_up(o + (size_t)L.tiles * 4);
+    L.tile_last = o; o = sr_align_up(o + (size_t)L.tiles * 8 * 4);   // per 8x4 sub-tile: deepest contributor
     L.total = o;
     return L;
 }
@@ -171,6 +171,18 @@ cudaError_t launch_surfel_bwd(const BwdArgs& a);          // surfel_bwd.cu
 cudaError_t launch_mark_visible(int P, const float* means3D, const float* vm, uint8_t* present, cudaStream_t s);
 
 void sr_count_launch(int n = 1);
+
+// Optional per-kernel timing (sr_set_profiling): CUDA events recorded on the launching stream around each
+// kernel; read back (after a sync) with sr_get_profile().  Off by default: zero overhead on the hot path.
+bool sr_profiling_on();
+void sr_profile_push(const char* name, cudaEvent_t e0, cudaEvent_t e1);
+struct ProfileScope {
+    const char* name; cudaStream_t stream; cudaEvent_t e0 = nullptr, e1 = nullptr; bool on;
+    ProfileScope(const char* n, cudaStream_t s) : name(n), stream(s), on(sr_profiling_on()) {
+        if (on) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, stream); }
+    }
+    ~ProfileScope() { if (on) { cudaEventRecord(e1, stream); sr_profile_push(name, e0, e1); } }
+};
 
 // ---- small device helpers -----------------------------------------------------------------
 #ifdef __CUDACC__

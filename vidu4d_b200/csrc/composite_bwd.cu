@@ -4,25 +4,18 @@
 //
 // The reference issues up to 16 global float atomics per contributing (pixel, surfel) pair
 // (backward.cu:345-446).  Here (DESIGN.md "composite backward"):
-//   * same tiling / TMA-fed instance stream / sub-tile culling as the forward, walked back to front,
-//     starting at the tile's deepest contributor recorded by the forward (no work on the occluded tail);
-//   * the 16 per-pair gradient components are reduced across the 32 pixels of a warp with a
-//     recursive-halving butterfly (16 shuffles), the 16 lane-distributed sums go to a per-CTA
-//     shared-memory accumulator, and each (tile, instance, component) leaves the SM as ONE global
-//     reduction -- 16 per instance instead of 16 per contributing pixel.
-#include "common.cuh"
+//   * same tiling, warp-autonomous TMA-fed instance stream and sub-tile culling as the forward, walked back to
+//     front, starting at the sub-tile's deepest contributor recorded by the forward (no work on the occluded tail);
+//   * the 16 per-pair gradient components are reduced across the 32 pixels of a warp with a recursive-halving
+//     butterfly (16 shuffles) and leave the SM as ONE 16-lane global reduction per (sub-tile, instance) --
+//     64 contiguous bytes of the surfel's accumulator -- instead of 16 scalar atomics per contributing pixel.
+#include "composite_common.cuh"
 
 namespace {
-
-constexpr int CHUNK = 128;
-constexpr int NACC = 18;    // 0..8 dT, 9 dopacity, 10..12 dcolor, 13..15 dnormal, 16..17 dmean2D
-
-__device__ __forceinline__ float fm(float a, float b) { return __fmul_rn(a, b); }
-__device__ __forceinline__ float fa(float a, float b) { return __fadd_rn(a, b); }
-__device__ __forceinline__ float ff(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+using namespace comp;
 
 // recursive-halving sum of v[0..15] over the warp; afterwards lane L holds the total of component
-// comp(L) = 8*b4 + 4*b3 + 2*b2 + b1 (bits of L) in v[0]
+// comp(L) = 8*b4 + 4*b3 + 2*b2 + b1 (bits of L) in v[0] (both lanes of a pair hold the same total)
 __device__ __forceinline__ void butterfly16(float (&v)[16], int lane) {
     {
         const bool hi = lane & 16;
@@ -56,47 +49,52 @@ __device__ __forceinline__ void butterfly16(float (&v)[16], int lane) {
     v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
-__global__ void __launch_bounds__(256)
+// butterfly component index -> slot in the 20-float per-surfel accumulator (common.cuh SR_G_*):
+// v[] order: 0..8 dT, 9 dopacity, 10..12 dcolor, 13..15 dnormal
+__device__ __forceinline__ int comp_slot(int c) {
+    return c < 9 ? SR_G_T + c : (c == 9 ? SR_G_OPAC : (c < 13 ? SR_G_COLOR + (c - 10) : SR_G_NORMAL + (c - 13)));
+}
+
+__global__ void __launch_bounds__(256, 2)
 composite_bwd_kernel(const uint2* __restrict__ ranges, const float4* __restrict__ irec, int W, int H,
                      const float* __restrict__ bg, const float* __restrict__ final_Ts,
-                     const uint32_t* __restrict__ n_contrib, const uint32_t* __restrict__ tile_last,
+                     const uint32_t* __restrict__ n_contrib, const uint32_t* __restrict__ sub_last,
                      const float* __restrict__ dL_dpixels, const float* __restrict__ dL_dothers,
                      float* __restrict__ sgrad) {
-    __shared__ __align__(128) float4 stage[2][CHUNK * 5];
-    __shared__ __align__(8) uint64_t full_bar[2];
-    __shared__ float acc[CHUNK * NACC];
+    __shared__ __align__(128) float4 stage[8][NST][WB * REC4];
+    __shared__ __align__(8) uint64_t bars[8][NST];
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int tile = blockIdx.y * gridDim.x + blockIdx.x;
     const uint2 range = ranges[tile];
-    const int len = min((int)(range.y - range.x), (int)tile_last[tile]);   // nothing beyond the deepest contributor matters
-    const int nchunks = (len + CHUNK - 1) / CHUNK;
-    if (nchunks == 0) return;
+    // nothing beyond this sub-tile's deepest contributor matters
+    const int len = min((int)(range.y - range.x), (int)sub_last[tile * 8 + warp]);
+    const int nb = (len + WB - 1) / WB;
+    if (nb == 0) return;
 
     const int sx0 = (warp & 1) * 8, sy0 = (warp >> 1) * 4;
-    const int lx = sx0 + (lane & 7), ly = sy0 + (lane >> 3);
-    const int pix_x = blockIdx.x * SR_TILE + lx, pix_y = blockIdx.y * SR_TILE + ly;
+    const int pix_x = blockIdx.x * SR_TILE + sx0 + (lane & 7), pix_y = blockIdx.y * SR_TILE + sy0 + (lane >> 3);
     const bool inside = pix_x < W && pix_y < H;
     const float pixx = (float)pix_x + 0.5f, pixy = (float)pix_y + 0.5f;
     const size_t N = (size_t)W * H, pid = (size_t)W * pix_y + pix_x;
 
-    if (tid == 0) {
-        mbar_init(&full_bar[0], 1);
-        mbar_init(&full_bar[1], 1);
+    const float4* src = irec + (size_t)range.x * REC4;
+    uint64_t* bar = bars[warp];
+    float4 (*st)[WB * REC4] = stage[warp];
+    // the k-th consumed batch (k = 0,1,..) is b = nb-1-k; it lives in stage k % NST
+    auto issue = [&](int k) {   // lane 0 only
+        const int b = nb - 1 - k, s = k % NST;
+        const uint32_t bytes = (uint32_t)min(WB, len - b * WB) * 80u;
+        mbar_expect_tx(&bar[s], bytes);
+        bulk_g2s(st[s], src + (size_t)b * WB * REC4, bytes, &bar[s]);
+    };
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < NST; s++) mbar_init(&bar[s], 1);
         fence_mbar_init();
+        for (int k = 0; k < NST && k < nb; k++) issue(k);
     }
-    for (int i = tid; i < CHUNK * NACC; i += 256) acc[i] = 0.f;
-    __syncthreads();
-    const float4* src = irec + (size_t)range.x * 5;
-    // chunks are consumed from the last to the first; k-th consumed chunk (k = 0,1,..) is c = nchunks-1-k
-    if (tid == 0) {
-        for (int k = 0; k < 2 && k < nchunks; k++) {
-            const int c = nchunks - 1 - k;
-            const uint32_t bytes = (uint32_t)min(CHUNK, len - c * CHUNK) * 80u;
-            mbar_expect_tx(&full_bar[k], bytes);
-            bulk_g2s(stage[k], src + (size_t)c * CHUNK * 5, bytes, &full_bar[k]);
-        }
-    }
+    __syncwarp();
 
     // per-pixel state (backward.cu:192-249)
     const float T_final = inside ? final_Ts[pid] : 0.f;
@@ -122,159 +120,128 @@ composite_bwd_kernel(const uint2* __restrict__ ranges, const float4* __restrict_
     float last_alpha = 0.f, last_depth = 0.f, accum_depth_rec = 0.f, accum_alpha_rec = 0.f, last_dL_dT = 0.f;
     float accum_n0 = 0.f, accum_n1 = 0.f, accum_n2 = 0.f, last_n0 = 0.f, last_n1 = 0.f, last_n2 = 0.f;
 
-    // deepest list position any pixel of this warp needs
-    int warp_last = last_contributor;
+    for (int k = 0; k < nb; k++) {
+        const int b = nb - 1 - k, s = k % NST;
+        mbar_wait(&bar[s], (uint32_t)((k / NST) & 1));
+        const int cnt = min(WB, len - b * WB);
+        const float4* S = st[s];
+        uint32_t cull = 0;
+        if (lane < cnt) cull = __float_as_uint(S[lane * REC4 + 4].w);
+        const int cx0 = cull & 15, cx1 = (cull >> 4) & 15, cy0 = (cull >> 8) & 15, cy1 = (cull >> 12) & 15;
+        const bool hit = ((cull >> 16) & 1u) && cx0 <= sx0 + 7 && cx1 >= sx0 && cy0 <= sy0 + 3 && cy1 >= sy0;
+        uint32_t m = __ballot_sync(0xffffffffu, hit);
+        while (m) {
+            const int jj = 31 - __clz(m);
+            m &= ~(1u << jj);
+            const int pos = b * WB + jj;                       // == `contributor` after the decrement
+            float v[16];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) warp_last = max(warp_last, __shfl_xor_sync(0xffffffffu, warp_last, o));
+            for (int i = 0; i < 16; i++) v[i] = 0.f;
+            float m2x = 0.f, m2y = 0.f;
+            bool contrib = false, lowpass = false;
+            const float rho_cut = cull_rho_cut(__shfl_sync(0xffffffffu, cull, jj));   // warp-uniform, before any divergence
+            if (pos < last_contributor) {
+                const float4 r0 = S[jj * REC4], r1 = S[jj * REC4 + 1], r2 = S[jj * REC4 + 2];
+                // identical geometry / alpha arithmetic to the forward so that the skips agree
+                const float kx = ff(pixx, r1.z, -r0.x), ky = ff(pixx, r1.w, -r0.y), kz = ff(pixx, r2.x, -r0.z);
+                const float lx_ = ff(pixy, r1.z, -r0.w), ly_ = ff(pixy, r1.w, -r1.x), lz_ = ff(pixy, r2.x, -r1.y);
+                const float pz = ff(kx, ly_, -fm(ky, lx_));
+                const float ppx = ff(ky, lz_, -fm(kz, ly_));
+                const float ppy = ff(kz, lx_, -fm(kx, lz_));
+                float sx, sy;
+                div2_rn(ppx, ppy, pz, sx, sy);
+                const float rho3d = ff(sx, sx, fm(sy, sy));
+                const float dx = fa(r2.y, -pixx), dy = fa(r2.z, -pixy);
+                const float q2 = ff(dx, dx, fm(dy, dy));
+                const float rho2d = fa(q2, q2);
+                const float rho = fminf(rho3d, rho2d);
+                if (pz != 0.0f && !(rho > rho_cut)) {
+                    const float c_d = (rho3d <= rho2d) ? fa(r2.x, ff(r1.z, sx, fm(r1.w, sy))) : r2.x;
+                    const float power = fm(rho, -0.5f);
+                    const float G = expf(power);
+                    const float alpha = fminf(0.99f, fm(r2.w, G));
+                    if (!(c_d < 0.2f) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f)) {
+                        contrib = true;
+                        const float4 r3 = S[jj * REC4 + 3], r4 = S[jj * REC4 + 4];
+                        T = T / (1.f - alpha);
+                        const float aT = alpha * T;
+                        float dL_dalpha = 0.f;
+                        // colour
+                        accum_rec0 = last_alpha * last_color0 + (1.f - last_alpha) * accum_rec0;
+                        accum_rec1 = last_alpha * last_color1 + (1.f - last_alpha) * accum_rec1;
+                        accum_rec2 = last_alpha * last_color2 + (1.f - last_alpha) * accum_rec2;
+                        last_color0 = r3.w; last_color1 = r4.x; last_color2 = r4.y;
+                        dL_dalpha += (r3.w - accum_rec0) * dpix0 + (r4.x - accum_rec1) * dpix1 + (r4.y - accum_rec2) * dpix2;
+                        v[10] = aT * dpix0; v[11] = aT * dpix1; v[12] = aT * dpix2;
+                        // distortion / median
+                        float dL_dz = 0.f, dL_dweight = 0.f;
+                        const float m_d = map_depth(c_d);
+                        const float dmd_dd = map_depth_grad(c_d);
+                        if (pos == median_contributor - 1) { dL_dz += dL_dmedian_depth; dL_dweight += dL_dmax_dweight; }
+                        dL_dweight += (final_D2 + m_d * m_d * final_A - 2.f * m_d * final_D) * dL_dreg;
+                        dL_dalpha += dL_dweight - last_dL_dT;
+                        last_dL_dT = dL_dweight * alpha + (1.f - alpha) * last_dL_dT;
+                        const float dL_dmd = 2.0f * aT * (m_d * final_A - final_D) * dL_dreg;
+                        dL_dz += dL_dmd * dmd_dd;
+                        // depth, alpha
+                        accum_depth_rec = last_alpha * last_depth + (1.f - last_alpha) * accum_depth_rec;
+                        last_depth = c_d;
+                        dL_dalpha += (c_d - accum_depth_rec) * dL_ddepth;
+                        accum_alpha_rec = last_alpha + (1.f - last_alpha) * accum_alpha_rec;
+                        dL_dalpha += (1.f - accum_alpha_rec) * dL_daccum;
+                        // normal
+                        accum_n0 = last_alpha * last_n0 + (1.f - last_alpha) * accum_n0;
+                        accum_n1 = last_alpha * last_n1 + (1.f - last_alpha) * accum_n1;
+                        accum_n2 = last_alpha * last_n2 + (1.f - last_alpha) * accum_n2;
+                        last_n0 = r3.x; last_n1 = r3.y; last_n2 = r3.z;
+                        dL_dalpha += (r3.x - accum_n0) * dn0 + (r3.y - accum_n1) * dn1 + (r3.z - accum_n2) * dn2;
+                        v[13] = aT * dn0; v[14] = aT * dn1; v[15] = aT * dn2;
 
-    for (int k = 0; k < nchunks; k++) {
-        const int c = nchunks - 1 - k;
-        const int s = k & 1;
-        mbar_wait(&full_bar[s], (uint32_t)((k >> 1) & 1));
-        const int cnt = min(CHUNK, len - c * CHUNK);
-        const float4* S = stage[s];
-        const int base_pos = c * CHUNK;
-        if (base_pos < warp_last) {
-            const int top = min(cnt, warp_last - base_pos);           // positions >= warp_last are skipped by every lane
-            for (int b = ((top - 1) >> 5) << 5; b >= 0; b -= 32) {
-                const int j = b + lane;
-                uint32_t cull = 0;
-                if (j < top) cull = __float_as_uint(S[j * 5 + 4].w);
-                const int cx0 = cull & 15, cx1 = (cull >> 4) & 15, cy0 = (cull >> 8) & 15, cy1 = (cull >> 12) & 15;
-                const bool hit = (cull >> 16) && cx0 <= sx0 + 7 && cx1 >= sx0 && cy0 <= sy0 + 3 && cy1 >= sy0;
-                uint32_t m = __ballot_sync(0xffffffffu, hit);
-                while (m) {
-                    const int bit = 31 - __clz(m);
-                    m &= ~(1u << bit);
-                    const int jj = b + bit;
-                    const int pos = base_pos + jj;                     // == `contributor` after the decrement
-                    float v[16];
-#pragma unroll
-                    for (int i = 0; i < 16; i++) v[i] = 0.f;
-                    float m2x = 0.f, m2y = 0.f;
-                    bool contrib = false, lowpass = false;
-                    if (pos < last_contributor) {
-                        const float4 r0 = S[jj * 5], r1 = S[jj * 5 + 1], r2 = S[jj * 5 + 2];
-                        // identical geometry / alpha arithmetic to the forward so that the skips agree
-                        const float kx = ff(pixx, r1.z, -r0.x), ky = ff(pixx, r1.w, -r0.y), kz = ff(pixx, r2.x, -r0.z);
-                        const float lx_ = ff(pixy, r1.z, -r0.w), ly_ = ff(pixy, r1.w, -r1.x), lz_ = ff(pixy, r2.x, -r1.y);
-                        const float pz = ff(kx, ly_, -fm(ky, lx_));
-                        const float ppx = ff(ky, lz_, -fm(kz, ly_));
-                        const float ppy = ff(kz, lx_, -fm(kx, lz_));
-                        const float sx = __fdiv_rn(ppx, pz), sy = __fdiv_rn(ppy, pz);
-                        const float rho3d = ff(sx, sx, fm(sy, sy));
-                        const float dx = fa(r2.y, -pixx), dy = fa(r2.z, -pixy);
-                        const float q2 = ff(dx, dx, fm(dy, dy));
-                        const float rho2d = fa(q2, q2);
-                        const float rho = fminf(rho3d, rho2d);
-                        const float c_d = (rho3d <= rho2d) ? fa(r2.x, ff(r1.z, sx, fm(r1.w, sy))) : r2.x;
-                        const float power = fm(rho, -0.5f);
-                        const float G = expf(power);
-                        const float alpha = fminf(0.99f, fm(r2.w, G));
-                        if (pz != 0.0f && !(c_d < 0.2f) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f)) {
-                            contrib = true;
-                            const float4 r3 = S[jj * 5 + 3], r4 = S[jj * 5 + 4];
-                            T = T / (1.f - alpha);
-                            const float aT = alpha * T;
-                            float dL_dalpha = 0.f;
-                            // colour
-                            accum_rec0 = last_alpha * last_color0 + (1.f - last_alpha) * accum_rec0;
-                            accum_rec1 = last_alpha * last_color1 + (1.f - last_alpha) * accum_rec1;
-                            accum_rec2 = last_alpha * last_color2 + (1.f - last_alpha) * accum_rec2;
-                            last_color0 = r3.w; last_color1 = r4.x; last_color2 = r4.y;
-                            dL_dalpha += (r3.w - accum_rec0) * dpix0 + (r4.x - accum_rec1) * dpix1 + (r4.y - accum_rec2) * dpix2;
-                            v[10] = aT * dpix0; v[11] = aT * dpix1; v[12] = aT * dpix2;
-                            // distortion / median (the reference does this mapping in double, backward.cu:351-352)
-                            float dL_dz = 0.f, dL_dweight = 0.f;
-                            const double cdd = (double)c_d;
-                            const float m_d = (float)(fma(cdd, 100.0, -20.0) / (99.8 * cdd));
-                            const float dmd_dd = (float)(20.0 / (99.8 * cdd * cdd));
-                            if (pos == median_contributor - 1) { dL_dz += dL_dmedian_depth; dL_dweight += dL_dmax_dweight; }
-                            dL_dweight += (final_D2 + m_d * m_d * final_A - 2.f * m_d * final_D) * dL_dreg;
-                            dL_dalpha += dL_dweight - last_dL_dT;
-                            last_dL_dT = dL_dweight * alpha + (1.f - alpha) * last_dL_dT;
-                            const float dL_dmd = 2.0f * aT * (m_d * final_A - final_D) * dL_dreg;
-                            dL_dz += dL_dmd * dmd_dd;
-                            // depth, alpha
-                            accum_depth_rec = last_alpha * last_depth + (1.f - last_alpha) * accum_depth_rec;
-                            last_depth = c_d;
-                            dL_dalpha += (c_d - accum_depth_rec) * dL_ddepth;
-                            accum_alpha_rec = last_alpha + (1.f - last_alpha) * accum_alpha_rec;
-                            dL_dalpha += (1.f - accum_alpha_rec) * dL_daccum;
-                            // normal
-                            accum_n0 = last_alpha * last_n0 + (1.f - last_alpha) * accum_n0;
-                            accum_n1 = last_alpha * last_n1 + (1.f - last_alpha) * accum_n1;
-                            accum_n2 = last_alpha * last_n2 + (1.f - last_alpha) * accum_n2;
-                            last_n0 = r3.x; last_n1 = r3.y; last_n2 = r3.z;
-                            dL_dalpha += (r3.x - accum_n0) * dn0 + (r3.y - accum_n1) * dn1 + (r3.z - accum_n2) * dn2;
-                            v[13] = aT * dn0; v[14] = aT * dn1; v[15] = aT * dn2;
-
-                            dL_dalpha *= T;
-                            last_alpha = alpha;
-                            dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
-                            const float dL_dG = r2.w * dL_dalpha;
-                            dL_dz += aT * dL_ddepth;
-                            if (rho3d <= rho2d) {
-                                const float dL_dsx = dL_dG * -G * sx + dL_dz * r1.z;
-                                const float dL_dsy = dL_dG * -G * sy + dL_dz * r1.w;
-                                const float dsx_pz = dL_dsx / pz, dsy_pz = dL_dsy / pz;
-                                const float dpx = dsx_pz, dpy = dsy_pz, dpz = -(dsx_pz * sx + dsy_pz * sy);
-                                // dL_dk = l x dL_dp ; dL_dl = dL_dp x k
-                                const float dkx = ly_ * dpz - lz_ * dpy, dky = lz_ * dpx - lx_ * dpz, dkz = lx_ * dpy - ly_ * dpx;
-                                const float dlx = dpy * kz - dpz * ky, dly = dpz * kx - dpx * kz, dlz = dpx * ky - dpy * kx;
-                                v[0] = -dkx; v[1] = -dky; v[2] = -dkz;
-                                v[3] = -dlx; v[4] = -dly; v[5] = -dlz;
-                                v[6] = pixx * dkx + pixy * dlx + dL_dz * sx;
-                                v[7] = pixx * dky + pixy * dly + dL_dz * sy;
-                                v[8] = pixx * dkz + pixy * dlz + dL_dz;
-                            } else {
-                                lowpass = true;
-                                m2x = dL_dG * (-G * 2.0f * dx);
-                                m2y = dL_dG * (-G * 2.0f * dy);
-                                v[8] = dL_dz;
-                            }
-                            v[9] = G * dL_dalpha;
+                        dL_dalpha *= T;
+                        last_alpha = alpha;
+                        dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
+                        const float dL_dG = r2.w * dL_dalpha;
+                        dL_dz += aT * dL_ddepth;
+                        if (rho3d <= rho2d) {
+                            const float dL_dsx = dL_dG * -G * sx + dL_dz * r1.z;
+                            const float dL_dsy = dL_dG * -G * sy + dL_dz * r1.w;
+                            const float rpz = 1.0f / pz;
+                            const float dpx = dL_dsx * rpz, dpy = dL_dsy * rpz, dpz = -(dpx * sx + dpy * sy);
+                            // dL_dk = l x dL_dp ; dL_dl = dL_dp x k
+                            const float dkx = ly_ * dpz - lz_ * dpy, dky = lz_ * dpx - lx_ * dpz, dkz = lx_ * dpy - ly_ * dpx;
+                            const float dlx = dpy * kz - dpz * ky, dly = dpz * kx - dpx * kz, dlz = dpx * ky - dpy * kx;
+                            v[0] = -dkx; v[1] = -dky; v[2] = -dkz;
+                            v[3] = -dlx; v[4] = -dly; v[5] = -dlz;
+                            v[6] = pixx * dkx + pixy * dlx + dL_dz * sx;
+                            v[7] = pixx * dky + pixy * dly + dL_dz * sy;
+                            v[8] = pixx * dkz + pixy * dlz + dL_dz;
+                        } else {
+                            lowpass = true;
+                            m2x = dL_dG * (-G * 2.0f * dx);
+                            m2y = dL_dG * (-G * 2.0f * dy);
+                            v[8] = dL_dz;
                         }
-                    }
-                    if (__any_sync(0xffffffffu, contrib)) {
-                        butterfly16(v, lane);
-                        if ((lane & 1) == 0) atomicAdd(&acc[jj * NACC + (lane >> 1)], v[0]);
-                        if (__any_sync(0xffffffffu, lowpass)) {
-#pragma unroll
-                            for (int o = 16; o > 0; o >>= 1) {
-                                m2x += __shfl_xor_sync(0xffffffffu, m2x, o);
-                                m2y += __shfl_xor_sync(0xffffffffu, m2y, o);
-                            }
-                            if (lane == 0) { atomicAdd(&acc[jj * NACC + 16], m2x); atomicAdd(&acc[jj * NACC + 17], m2y); }
-                        }
+                        v[9] = G * dL_dalpha;
                     }
                 }
             }
-        }
-        __syncthreads();
-        // flush this chunk's accumulators: one global reduction per (instance, component)
-        for (int i = tid; i < cnt * NACC; i += 256) {
-            const float g = acc[i];
-            if (g != 0.f) {
-                const int j = i / NACC, comp = i - j * NACC;
-                const uint32_t id = __float_as_uint(S[j * 5 + 4].z);
-                // acc component -> sgrad slot
-                const int slot = comp < 9 ? SR_G_T + comp
-                               : comp == 9 ? SR_G_OPAC
-                               : comp < 13 ? SR_G_COLOR + (comp - 10)
-                               : comp < 16 ? SR_G_NORMAL + (comp - 13)
-                               : SR_G_M2D + (comp - 16);
-                atomicAdd(&sgrad[(size_t)id * SR_GRAD_FLOATS + slot], g);
-                acc[i] = 0.f;
+            if (__any_sync(0xffffffffu, contrib)) {
+                const uint32_t id = __float_as_uint(S[jj * REC4 + 4].z);
+                float* g = sgrad + (size_t)id * SR_GRAD_FLOATS;
+                butterfly16(v, lane);
+                if ((lane & 1) == 0) atomicAdd(g + comp_slot(lane >> 1), v[0]);
+                if (__any_sync(0xffffffffu, lowpass)) {
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        m2x += __shfl_xor_sync(0xffffffffu, m2x, o);
+                        m2y += __shfl_xor_sync(0xffffffffu, m2y, o);
+                    }
+                    if (lane == 0) { atomicAdd(g + SR_G_M2D, m2x); atomicAdd(g + SR_G_M2D + 1, m2y); }
+                }
             }
         }
-        __syncthreads();
-        if (tid == 0 && k + 2 < nchunks) {
-            const int cn = nchunks - 1 - (k + 2);
-            const uint32_t bytes = (uint32_t)min(CHUNK, len - cn * CHUNK) * 80u;
-            mbar_expect_tx(&full_bar[s], bytes);
-            bulk_g2s(stage[s], src + (size_t)cn * CHUNK * 5, bytes, &full_bar[s]);
-        }
+        __syncwarp();
+        if (lane == 0 && k + NST < nb) issue(k + NST);
     }
 }
 
@@ -284,6 +251,7 @@ cudaError_t launch_composite_bwd(const BwdArgs& a) {
     cudaError_t e = cudaMemsetAsync(a.geom + a.gl.sgrad, 0, (size_t)(a.cam.P > 0 ? a.cam.P : 1) * SR_GRAD_FLOATS * 4, a.stream);
     if (e != cudaSuccess) return e;
     dim3 grid(a.il.tiles_x, a.il.tiles_y, 1);
+    ProfileScope ps("composite_bwd", a.stream);
     composite_bwd_kernel<<<grid, 256, 0, a.stream>>>(
         (const uint2*)(a.img + a.il.ranges), (const float4*)(a.bin + a.bl.inst_rec), a.cam.W, a.cam.H, a.cam.bg,
         (const float*)(a.img + a.il.final_T), (const uint32_t*)(a.img + a.il.n_contrib),

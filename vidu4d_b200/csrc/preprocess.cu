@@ -357,6 +357,7 @@ __global__ void mark_visible_kernel(int P, const float* __restrict__ means3D, co
 
 cudaError_t launch_preprocess_fwd(const FwdArgs& a) {
     const int nb = a.gl.nblocks;
+    ProfileScope ps("preprocess_fwd", a.stream);
     preprocess_fwd_kernel<<<nb, 256, 0, a.stream>>>(
         a.cam, a.means3D, a.shs, a.colors_precomp, a.opacities, (const float2*)a.scales, (const float4*)a.rotations,
         a.radii, (float4*)(a.geom + a.gl.surfel_rec), (float*)(a.geom + a.gl.depths),
@@ -369,7 +370,9 @@ cudaError_t launch_preprocess_fwd(const FwdArgs& a) {
 cudaError_t launch_scan_emit(const FwdArgs& a) {
     const int nb = a.gl.nblocks;
     uint32_t* bs = (uint32_t*)(a.geom + a.gl.block_sums);
-    scan_block_sums_kernel<<<1, 1024, 0, a.stream>>>(bs, nb, a.num_rendered_dev, (long long)a.bl.capacity);
+    { ProfileScope ps("scan_block_sums", a.stream);
+      scan_block_sums_kernel<<<1, 1024, 0, a.stream>>>(bs, nb, a.num_rendered_dev, (long long)a.bl.capacity); }
+    ProfileScope ps("emit_keys", a.stream);
     emit_keys_kernel<<<nb, 256, 0, a.stream>>>(
         a.cam, (const float4*)(a.geom + a.gl.surfel_rec), (const float*)(a.geom + a.gl.depths), a.radii,
         (const uint32_t*)(a.geom + a.gl.tiles_touched), bs, (uint32_t*)(a.geom + a.gl.point_offsets),

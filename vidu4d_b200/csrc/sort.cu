@@ -234,7 +234,13 @@ ranges_gather_kernel(const uint64_t* __restrict__ keys0, const uint64_t* __restr
     const int x0 = max((int)(bx & 0xffffu) - tx, 0), x1 = min((int)(bx >> 16) - tx, SR_TILE - 1);
     const int y0 = max((int)(by & 0xffffu) - ty, 0), y1 = min((int)(by >> 16) - ty, SR_TILE - 1);
     uint32_t cull = 0;
-    if (x0 <= x1 && y0 <= y1) cull = (uint32_t)x0 | ((uint32_t)x1 << 4) | ((uint32_t)y0 << 8) | ((uint32_t)y1 << 12) | (1u << 16);
+    if (x0 <= x1 && y0 <= y1) {
+        // rho_cut: a (pixel, instance) pair with rho > rho_cut has opacity*exp(-rho/2) < 1/255 even after the
+        // 2-ulp error of expf and the rounding of the product; quantised UPWARDS to 1/1024 (14 bits)
+        const float c2 = 2.0f * logf(255.0f * a2.w) + 1e-4f;
+        const uint32_t q = (uint32_t)min(16383.0f, fmaxf(0.0f, ceilf(c2 * 1024.0f)));
+        cull = (uint32_t)x0 | ((uint32_t)x1 << 4) | ((uint32_t)y0 << 8) | ((uint32_t)y1 << 12) | (1u << 16) | (q << 17);
+    }
     a4.z = __uint_as_float(id);
     a4.w = __uint_as_float(cull);
     float4* o = irec + (size_t)i * 5;
@@ -266,8 +272,11 @@ cudaError_t launch_sort(const FwdArgs& a) {
     uint32_t* status = (uint32_t*)(a.bin + a.bl.status);
     const long long cap = (long long)a.bl.capacity;
     const int hblocks = (int)((cap + 4095) / 4096);
-    sort_histogram_kernel<<<hblocks, 256, 0, a.stream>>>(k0, a.num_rendered_dev, cap, plan, hist);
-    sort_plan_kernel<<<1, 256, 0, a.stream>>>(hist, ctl, a.num_rendered_dev, cap, plan);
+    { ProfileScope ps("sort_histogram", a.stream);
+      sort_histogram_kernel<<<hblocks, 256, 0, a.stream>>>(k0, a.num_rendered_dev, cap, plan, hist); }
+    { ProfileScope ps("sort_plan", a.stream);
+      sort_plan_kernel<<<1, 256, 0, a.stream>>>(hist, ctl, a.num_rendered_dev, cap, plan); }
+    ProfileScope ps("onesweep_passes", a.stream);
     for (int p = 0; p < plan.npass; p++)
         onesweep_pass_kernel<<<a.bl.sort_tiles, SR_SORT_THREADS, 0, a.stream>>>(
             k0, k1, v0, v1, hist, ctl, status, a.num_rendered_dev, p, plan.shift[p], plan.bits[p], a.bl.sort_tiles);
@@ -278,6 +287,7 @@ cudaError_t launch_sort(const FwdArgs& a) {
 cudaError_t launch_ranges_gather(const FwdArgs& a) {
     const long long cap = (long long)a.bl.capacity;
     const int blocks = (int)((cap + 255) / 256);
+    ProfileScope ps("ranges_gather", a.stream);
     ranges_gather_kernel<<<blocks, 256, 0, a.stream>>>(
         (const uint64_t*)(a.bin + a.bl.keys[0]), (const uint64_t*)(a.bin + a.bl.keys[1]),
         (const uint32_t*)(a.bin + a.bl.values[0]), (const uint32_t*)(a.bin + a.bl.values[1]),

@@ -205,6 +205,7 @@ surfel_bwd_kernel(const CamParams c, const float* __restrict__ means3D, const fl
 
 cudaError_t launch_surfel_bwd(const BwdArgs& a) {
     const int nb = a.gl.nblocks;
+    ProfileScope ps("surfel_bwd", a.stream);
     surfel_bwd_kernel<<<nb, 256, 0, a.stream>>>(
         a.cam, a.means3D, a.shs, (const float2*)a.scales, (const float4*)a.rotations, a.radii,
         (const float4*)(a.geom + a.gl.surfel_rec), (const uint8_t*)(a.geom + a.gl.clamped),

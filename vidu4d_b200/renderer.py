@@ -99,30 +99,30 @@ def make_camera(width, height, fovx, fovy, R=None, T=None, device="cuda", znear=
 # ---------------------------------------------------------------------------------------------
 # gs/utils/point_utils.py
 # ---------------------------------------------------------------------------------------------
-_ray_cache: dict = {}
+_dir_cache: dict = {}
 
 
 def _rays(view, device):
-    """rays_d (H*W,3) and rays_o (3,) of depths_to_points (point_utils.py:9-21), cached per camera so the
-    per-frame torch.tensor(...).cuda(), .inverse() and math.tan(cuda tensor) host syncs disappear."""
+    """rays_d (H*W,3) and rays_o (3,) of depths_to_points (point_utils.py:9-21).  The camera-space pixel
+    directions (pixel grid times K^-1) are cached per (W,H,fov); the per-frame camera-to-world factor uses
+    inv_ex (no error check => no host synchronisation), so the reference's per-call torch.tensor(...).cuda(),
+    .inverse() and math.tan(cuda tensor) syncs are gone."""
     W, H = int(view.image_width), int(view.image_height)
-    wvt = view.world_view_transform
-    key = (W, H, _tan_half(view.FoVx), _tan_half(view.FoVy), wvt.data_ptr(), wvt._version, str(device))
-    hit = _ray_cache.get(key)
-    if hit is not None:
-        return hit
-    c2w = (wvt.T).inverse()
-    fx = W / (2 * _tan_half(view.FoVx))
-    fy = H / (2 * _tan_half(view.FoVy))
-    intrins = torch.tensor([[fx, 0., W / 2.], [0., fy, H / 2.], [0., 0., 1.0]], dtype=torch.float32, device=device)
-    grid_x, grid_y = torch.meshgrid(torch.arange(W, device=device).float(), torch.arange(H, device=device).float(),
-                                    indexing='xy')
-    points = torch.stack([grid_x, grid_y, torch.ones_like(grid_x)], dim=-1).reshape(-1, 3)
-    rays_d = points @ intrins.inverse().T @ c2w[:3, :3].T
+    tx, ty = _tan_half(view.FoVx), _tan_half(view.FoVy)
+    key = (W, H, tx, ty, str(device))
+    dirs = _dir_cache.get(key)
+    if dirs is None:
+        fx, fy = W / (2 * tx), H / (2 * ty)
+        intrins = torch.tensor([[fx, 0., W / 2.], [0., fy, H / 2.], [0., 0., 1.0]], dtype=torch.float32)
+        grid_x, grid_y = torch.meshgrid(torch.arange(W).float(), torch.arange(H).float(), indexing='xy')
+        points = torch.stack([grid_x, grid_y, torch.ones_like(grid_x)], dim=-1).reshape(-1, 3)
+        dirs = (points @ intrins.inverse().T).to(device)
+        if len(_dir_cache) > 16:
+            _dir_cache.clear()
+        _dir_cache[key] = dirs
+    c2w = torch.linalg.inv_ex(view.world_view_transform.T, check_errors=False).inverse
+    rays_d = dirs @ c2w[:3, :3].T
     rays_o = c2w[:3, 3]
-    if len(_ray_cache) > 64:
-        _ray_cache.clear()
-    _ray_cache[key] = (rays_d, rays_o)
     return rays_d, rays_o
 
 

@@ -55,7 +55,7 @@ __device__ __forceinline__ int comp_slot(int c) {
     return c < 9 ? SR_G_T + c : (c == 9 ? SR_G_OPAC : (c < 13 ? SR_G_COLOR + (c - 10) : SR_G_NORMAL + (c - 13)));
 }
 
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, 3)
 composite_bwd_kernel(const uint2* __restrict__ ranges, const float4* __restrict__ irec, int W, int H,
                      const float* __restrict__ bg, const float* __restrict__ final_Ts,
                      const uint32_t* __restrict__ n_contrib, const uint32_t* __restrict__ sub_last,

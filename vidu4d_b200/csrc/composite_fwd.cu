@@ -69,17 +69,16 @@ composite_fwd_kernel(const uint2* __restrict__ ranges, const float4* __restrict_
         const int cx0 = cull & 15, cx1 = (cull >> 4) & 15, cy0 = (cull >> 8) & 15, cy1 = (cull >> 12) & 15;
         const bool hit = ((cull >> 16) & 1u) && cx0 <= sx0 + 7 && cx1 >= sx0 && cy0 <= sy0 + 3 && cy1 >= sy0;
         uint32_t m = __ballot_sync(0xffffffffu, hit);
-        while (m) {
-            const int jj = __ffs(m) - 1;
-            m &= m - 1;
-            const float rho_cut = cull_rho_cut(__shfl_sync(0xffffffffu, cull, jj));   // warp-uniform, before any divergence
-            if (done) continue;
+        // Geometry + alpha of one (pixel, instance) pair; independent of the running transmittance, so two
+        // survivors are evaluated per iteration for instruction-level parallelism and then blended in list order.
+        auto eval = [&](int jj, float rho_cut, float& alpha, float& depth) {
+            alpha = 0.f; depth = 0.f;
             const float4 r0 = S[jj * REC4], r1 = S[jj * REC4 + 1], r2 = S[jj * REC4 + 2];
             // T rows: Tu=(r0.x,r0.y,r0.z) Tv=(r0.w,r1.x,r1.y) Tw=(r1.z,r1.w,r2.x); xy=(r2.y,r2.z); opac=r2.w
             const float kx = ff(pixx, r1.z, -r0.x), ky = ff(pixx, r1.w, -r0.y), kz = ff(pixx, r2.x, -r0.z);
             const float lx_ = ff(pixy, r1.z, -r0.w), ly_ = ff(pixy, r1.w, -r1.x), lz_ = ff(pixy, r2.x, -r1.y);
             const float pz = ff(kx, ly_, -fm(ky, lx_));
-            if (pz == 0.0f) continue;
+            if (pz == 0.0f) return;
             const float ppx = ff(ky, lz_, -fm(kz, ly_));
             const float ppy = ff(kz, lx_, -fm(kx, lz_));
             float sx, sy;
@@ -89,15 +88,18 @@ composite_fwd_kernel(const uint2* __restrict__ ranges, const float4* __restrict_
             const float q2 = ff(dx, dx, fm(dy, dy));
             const float rho2d = fa(q2, q2);
             const float rho = fminf(rho3d, rho2d);
-            if (rho > rho_cut) continue;                 // alpha < 1/255 guaranteed: same outcome as below, no expf
-            const float depth = (rho3d <= rho2d) ? fa(r2.x, ff(r1.z, sx, fm(r1.w, sy))) : r2.x;
-            if (depth < 0.2f) continue;
+            if (rho > rho_cut) return;                   // alpha < 1/255 guaranteed: same outcome as below, no expf
+            const float d = (rho3d <= rho2d) ? fa(r2.x, ff(r1.z, sx, fm(r1.w, sy))) : r2.x;
+            if (d < 0.2f) return;
             const float power = fm(rho, -0.5f);
-            if (power > 0.0f) continue;
-            const float alpha = fminf(0.99f, fm(r2.w, expf(power)));
-            if (alpha < 1.0f / 255.0f) continue;
+            if (power > 0.0f) return;
+            const float al = fminf(0.99f, fm(r2.w, expf(power)));
+            if (al < 1.0f / 255.0f) return;
+            alpha = al; depth = d;
+        };
+        auto blend = [&](int jj, float alpha, float depth) {
             const float test_T = fm(T, fa(1.0f, -alpha));
-            if (test_T < 0.0001f) { done = true; continue; }
+            if (test_T < 0.0001f) { done = true; return; }
             const float4 r3 = S[jj * REC4 + 3], r4 = S[jj * REC4 + 4];
             const uint32_t contributor = (uint32_t)(b * WB + jj + 1);
             const float A = fa(1.0f, -T);
@@ -117,6 +119,22 @@ composite_fwd_kernel(const uint2* __restrict__ ranges, const float4* __restrict_
             C2 = ff(T, fm(alpha, r4.y), C2);
             T = test_T;
             last_contributor = contributor;
+        };
+        while (m) {
+            const int j0 = __ffs(m) - 1;
+            m &= m - 1;
+            const bool two = m != 0;
+            const int j1 = two ? __ffs(m) - 1 : j0;
+            m &= m - 1;                                   // no-op when m == 0
+            // warp-uniform, before any divergence
+            const float rc0 = cull_rho_cut(__shfl_sync(0xffffffffu, cull, j0));
+            const float rc1 = cull_rho_cut(__shfl_sync(0xffffffffu, cull, j1));
+            if (done) continue;
+            float a0, d0, a1 = 0.f, d1 = 0.f;
+            eval(j0, rc0, a0, d0);
+            if (two) eval(j1, rc1, a1, d1);
+            if (a0 != 0.f) blend(j0, a0, d0);
+            if (a1 != 0.f && !done) blend(j1, a1, d1);
         }
         __syncwarp();                                   // every lane is done reading stage s
         if (__all_sync(0xffffffffu, done)) {

@@ -183,6 +183,7 @@ int sr_forward(const sr_frame* f, const float* background, const float* means3D,
     CK(launch_scan_emit(a), "scan/emit_keys"); DBG("scan/emit_keys");
     CK(launch_sort(a), "sort"); DBG("sort");
     CK(launch_ranges_gather(a), "ranges_gather"); DBG("ranges_gather");
+    CK(launch_tile_order(a), "tile_order"); DBG("tile_order");
     CK(launch_composite_fwd(a), "composite_fwd"); DBG("composite_fwd");
     if (num_rendered_host)
         CK(cudaMemcpyAsync(num_rendered_host, num_rendered_dev, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream), "copy(num_rendered)");

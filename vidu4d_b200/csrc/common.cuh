@@ -62,7 +62,7 @@ struct GeomLayout {
     int nblocks;
 };
 struct ImageLayout {
-    size_t final_T, n_contrib, ranges, tile_last, total;
+    size_t final_T, n_contrib, ranges, tile_last, tile_order, total;
     int tiles_x, tiles_y, tiles;
 };
 struct BinLayout {
@@ -94,6 +94,7 @@ static inline __host__ __device__ ImageLayout image_layout(int W, int H) {
     L.n_contrib = o; o = sr_align_up(o + 2 * N * 4);
     L.ranges = o;    o = sr_align_up(o + (size_t)L.tiles * 8);
     L.tile_last = o; o = sr_align_up(o + (size_t)L.tiles * 8 * 4);   // per 8x4 sub-tile: deepest contributor
+    L.tile_order = o; o = sr_align_up(o + (size_t)L.tiles * 4);       // tiles, longest instance list first
     L.total = o;
     return L;
 }
@@ -165,6 +166,7 @@ cudaError_t launch_preprocess_fwd(const FwdArgs& a);      // preprocess.cu
 cudaError_t launch_scan_emit(const FwdArgs& a);           // preprocess.cu
 cudaError_t launch_sort(const FwdArgs& a);                // sort.cu
 cudaError_t launch_ranges_gather(const FwdArgs& a);       // sort.cu
+cudaError_t launch_tile_order(const FwdArgs& a);          // sort.cu
 cudaError_t launch_composite_fwd(const FwdArgs& a);       // composite_fwd.cu
 cudaError_t launch_composite_bwd(const BwdArgs& a);       // composite_bwd.cu
 cudaError_t launch_surfel_bwd(const BwdArgs& a);          // surfel_bwd.cu

@@ -55,17 +55,20 @@ __device__ __forceinline__ int comp_slot(int c) {
     return c < 9 ? SR_G_T + c : (c == 9 ? SR_G_OPAC : (c < 13 ? SR_G_COLOR + (c - 10) : SR_G_NORMAL + (c - 13)));
 }
 
-__global__ void __launch_bounds__(256, 3)
-composite_bwd_kernel(const uint2* __restrict__ ranges, const float4* __restrict__ irec, int W, int H,
+__global__ void __launch_bounds__(32, 24)
+composite_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order, int tiles_x,
+                     const float4* __restrict__ irec, int W, int H,
                      const float* __restrict__ bg, const float* __restrict__ final_Ts,
                      const uint32_t* __restrict__ n_contrib, const uint32_t* __restrict__ sub_last,
                      const float* __restrict__ dL_dpixels, const float* __restrict__ dL_dothers,
                      float* __restrict__ sgrad) {
-    __shared__ __align__(128) float4 stage[8][NST][WB * REC4];
-    __shared__ __align__(8) uint64_t bars[8][NST];
+    // one warp per CTA: work item = (tile, 8x4 sub-tile), tiles in longest-list-first order
+    __shared__ __align__(128) float4 st[NST][WB * REC4];
+    __shared__ __align__(8) uint64_t bar[NST];
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+    const int lane = threadIdx.x, warp = blockIdx.x & 7;
+    const int tile = (int)tile_order[blockIdx.x >> 3];
+    const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
     const uint2 range = ranges[tile];
     // nothing beyond this sub-tile's deepest contributor matters
     const int len = min((int)(range.y - range.x), (int)sub_last[tile * 8 + warp]);
@@ -73,14 +76,12 @@ composite_bwd_kernel(const uint2* __restrict__ ranges, const float4* __restrict_
     if (nb == 0) return;
 
     const int sx0 = (warp & 1) * 8, sy0 = (warp >> 1) * 4;
-    const int pix_x = blockIdx.x * SR_TILE + sx0 + (lane & 7), pix_y = blockIdx.y * SR_TILE + sy0 + (lane >> 3);
+    const int pix_x = tile_x * SR_TILE + sx0 + (lane & 7), pix_y = tile_y * SR_TILE + sy0 + (lane >> 3);
     const bool inside = pix_x < W && pix_y < H;
     const float pixx = (float)pix_x + 0.5f, pixy = (float)pix_y + 0.5f;
     const size_t N = (size_t)W * H, pid = (size_t)W * pix_y + pix_x;
 
     const float4* src = irec + (size_t)range.x * REC4;
-    uint64_t* bar = bars[warp];
-    float4 (*st)[WB * REC4] = stage[warp];
     // the k-th consumed batch (k = 0,1,..) is b = nb-1-k; it lives in stage k % NST
     auto issue = [&](int k) {   // lane 0 only
         const int b = nb - 1 - k, s = k % NST;
@@ -250,10 +251,10 @@ composite_bwd_kernel(const uint2* __restrict__ ranges, const float4* __restrict_
 cudaError_t launch_composite_bwd(const BwdArgs& a) {
     cudaError_t e = cudaMemsetAsync(a.geom + a.gl.sgrad, 0, (size_t)(a.cam.P > 0 ? a.cam.P : 1) * SR_GRAD_FLOATS * 4, a.stream);
     if (e != cudaSuccess) return e;
-    dim3 grid(a.il.tiles_x, a.il.tiles_y, 1);
     ProfileScope ps("composite_bwd", a.stream);
-    composite_bwd_kernel<<<grid, 256, 0, a.stream>>>(
-        (const uint2*)(a.img + a.il.ranges), (const float4*)(a.bin + a.bl.inst_rec), a.cam.W, a.cam.H, a.cam.bg,
+    composite_bwd_kernel<<<a.il.tiles * 8, 32, 0, a.stream>>>(
+        (const uint2*)(a.img + a.il.ranges), (const uint32_t*)(a.img + a.il.tile_order), a.il.tiles_x,
+        (const float4*)(a.bin + a.bl.inst_rec), a.cam.W, a.cam.H, a.cam.bg,
         (const float*)(a.img + a.il.final_T), (const uint32_t*)(a.img + a.il.n_contrib),
         (const uint32_t*)(a.img + a.il.tile_last), a.dL_dcolor, a.dL_dothers, (float*)(a.geom + a.gl.sgrad));
     sr_count_launch();

@@ -18,28 +18,29 @@
 namespace {
 using namespace comp;
 
-__global__ void __launch_bounds__(256)
-composite_fwd_kernel(const uint2* __restrict__ ranges, const float4* __restrict__ irec, int W, int H,
+__global__ void __launch_bounds__(32)
+composite_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order, int tiles_x,
+                     const float4* __restrict__ irec, int W, int H,
                      const float* __restrict__ bg, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
                      float* __restrict__ out_color, float* __restrict__ out_others, uint32_t* __restrict__ sub_last) {
-    __shared__ __align__(128) float4 stage[8][NST][WB * REC4];
-    __shared__ __align__(8) uint64_t bars[8][NST];
+    // one warp per CTA: work item = (tile, 8x4 sub-tile), tiles in longest-list-first order
+    __shared__ __align__(128) float4 st[NST][WB * REC4];
+    __shared__ __align__(8) uint64_t bar[NST];
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+    const int lane = threadIdx.x, warp = blockIdx.x & 7;
+    const int tile = (int)tile_order[blockIdx.x >> 3];
+    const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
     const uint2 range = ranges[tile];
     const int len = (int)(range.y - range.x);
     const int nb = (len + WB - 1) / WB;
 
     // warp -> 8x4 sub-tile, lane -> pixel
     const int sx0 = (warp & 1) * 8, sy0 = (warp >> 1) * 4;
-    const int pix_x = blockIdx.x * SR_TILE + sx0 + (lane & 7), pix_y = blockIdx.y * SR_TILE + sy0 + (lane >> 3);
+    const int pix_x = tile_x * SR_TILE + sx0 + (lane & 7), pix_y = tile_y * SR_TILE + sy0 + (lane >> 3);
     const bool inside = pix_x < W && pix_y < H;
     const float pixx = (float)pix_x + 0.5f, pixy = (float)pix_y + 0.5f;
 
     const float4* src = irec + (size_t)range.x * REC4;
-    uint64_t* bar = bars[warp];
-    float4 (*st)[WB * REC4] = stage[warp];
     auto issue = [&](int b) {   // lane 0 only
         const int s = b % NST;
         const uint32_t bytes = (uint32_t)min(WB, len - b * WB) * 80u;
@@ -175,10 +176,10 @@ composite_fwd_kernel(const uint2* __restrict__ ranges, const float4* __restrict_
 }  // namespace
 
 cudaError_t launch_composite_fwd(const FwdArgs& a) {
-    dim3 grid(a.il.tiles_x, a.il.tiles_y, 1);
     ProfileScope ps("composite_fwd", a.stream);
-    composite_fwd_kernel<<<grid, 256, 0, a.stream>>>(
-        (const uint2*)(a.img + a.il.ranges), (const float4*)(a.bin + a.bl.inst_rec), a.cam.W, a.cam.H, a.cam.bg,
+    composite_fwd_kernel<<<a.il.tiles * 8, 32, 0, a.stream>>>(
+        (const uint2*)(a.img + a.il.ranges), (const uint32_t*)(a.img + a.il.tile_order), a.il.tiles_x,
+        (const float4*)(a.bin + a.bl.inst_rec), a.cam.W, a.cam.H, a.cam.bg,
         (float*)(a.img + a.il.final_T), (uint32_t*)(a.img + a.il.n_contrib), a.out_color, a.out_others,
         (uint32_t*)(a.img + a.il.tile_last));
     sr_count_launch();

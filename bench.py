@@ -58,6 +58,7 @@ def parse():
     ap.add_argument("--cpu-frames", type=int, default=2, help="frames of the cpu_baseline sample (0 = skip)")
     ap.add_argument("--no-ref-cuda", action="store_true", help="skip timing the reference extension in the ours arm")
     ap.add_argument("--ref-device", default="cuda", choices=["cuda", "cpu"])
+    ap.add_argument("--no-graph", action="store_true", help="keep the e2e step eager (no CUDA-graph capture)")
     return ap.parse_args()
 
 
@@ -129,7 +130,20 @@ def max_over_ranks(ms: float, world: int, device) -> float:
 
 
 # ------------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The ONE JSON line goes to the process's real stdout; everything else (NCCL banners, library chatter) was
+    rerouted to stderr at the file-descriptor level in main()."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)                     # C libraries (NCCL prints its version banner on stdout) now write to stderr
     args = parse()
     rank, world, local_rank = D.env_rank_world()
     if args.impl == "reference" and (args.ref_device == "cpu" or not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "_C.so"))):
@@ -257,27 +271,68 @@ def main():
     h2d = targets_h.numel() * 4 + cam_h.numel() * 4 + cps_hh.numel() * 4
     fov = 2.0 * float(np.arctan(TAN))
 
-    def step_e2e(step):
+    tg = torch.empty((F, 3, RES, RES), device=device); cam = torch.empty((F, 2, 4, 4), device=device); cp = torch.empty((F, 3), device=device)
+    tot = torch.zeros((), device=device)
+
+    def fill_host(step):
         for f in range(F):
             v = view_of(step, f)
             cam_h[f, 0] = torch.from_numpy(vms_h[v]); cam_h[f, 1] = torch.from_numpy(pms_h[v]); cps_hh[f] = torch.from_numpy(cps_h[v])
-        tg = targets_h.to(device, non_blocking=True); cam = cam_h.to(device, non_blocking=True); cp = cps_hh.to(device, non_blocking=True)
+
+    def body():
+        """H2D of this step's inputs -> render x F -> loss -> backward (everything a CUDA graph can hold)."""
+        tg.copy_(targets_h, non_blocking=True); cam.copy_(cam_h, non_blocking=True); cp.copy_(cps_hh, non_blocking=True)
         fg.zero_()
-        tot = torch.zeros((), device=device)
+        tot.zero_()
         for f in range(F):
             view = MiniCam(RES, RES, fov, fov, 0.01, 100.0, cam[f, 0], cam[f, 1], cp[f])
             out = render(view, cloud, pipe, bg)
             loss = (out["render"] - tg[f]).abs().mean() + 0.05 * (1.0 - (out["rend_normal"] * out["surf_normal"]).sum(0)).mean() \
                 + 0.01 * out["rend_dist"].mean()
             loss.backward()
-            tot += loss.detach()
+            tot.add_(loss.detach())
+
+    def tail():
         fg.allreduce_(average_over=F * world)
         opt.step()
         loss_h.copy_(tot.reshape(1), non_blocking=True)
         torch.cuda.current_stream().synchronize()
         if args.impl == "ours":
-            RZ.check_overflow()
+            RZ.check_overflow(keep=graph is not None)
         return float(loss_h[0])
+
+    graph, e2e_mode = None, "eager"
+
+    def step_e2e(step):
+        fill_host(step)
+        if graph is not None:
+            graph.replay()
+        else:
+            body()
+        return tail()
+
+    if args.impl == "ours" and not args.no_graph:
+        # The sync-free forward makes the whole step capturable: one cudaGraphLaunch replaces ~150 small launches.
+        # (The reference cannot be captured: its forward blocks on a D2H copy, rasterizer_impl.cu:282.)
+        try:
+            for s_ in range(2):
+                step_e2e(s_)                                   # eager warm-up: allocator pools, caches, capacity hints
+            RZ.check_overflow()
+            RZ.reserve_host_slots(F + 4)
+            gph = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream(device=device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                fill_host(0); body(); RZ.check_overflow()       # once on the side stream, as torch recommends
+            torch.cuda.current_stream().wait_stream(side)
+            RZ.reserve_host_slots(F + 4)
+            with torch.cuda.graph(gph):
+                body()
+            graph, e2e_mode = gph, "cuda_graph(H2D+render+loss+backward) + eager all-reduce/Adam/readback"
+        except Exception as ex:   # pragma: no cover
+            sys.stderr.write(f"[bench] CUDA-graph capture of the e2e step failed, staying eager: {ex!r}\n")
+            graph = None
+            RZ._pending.clear()
 
     e2e_total, _, _ = timed(step_e2e, K, Wm)
     e2e_total = max_over_ranks(e2e_total, world, device)
@@ -363,6 +418,7 @@ def main():
                        "parallelism": f"frames sharded over {world} GPU(s), 1 NCCL all-reduce of {acc_flat_bytes >> 20} MiB/step" if world > 1 else "1 GPU",
                        "l2": f"explicit flush (256 MiB write) between timed steps; per-step working set also exceeds the {L2_MB} MB L2"},
             "e2e": {"value": round(e2e_value, 2), "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
+                    "mode": e2e_mode,
                     "what": "render() -> L1+normal+distortion loss -> backward -> (all-reduce) -> fused Adam; per step the "
                             "cameras + target images come from pinned host memory, the loss is read back"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels_ms": kernels,
@@ -373,7 +429,7 @@ def main():
                                     "sample": "the reference's only implementation of this path is CUDA: this arm runs "
                                               "oracle/_ref/_C.so on the GPU (no CPU cores involved); see --ref-device cpu for the oracle port"}
             line["e2e"]["h2d_bytes_per_step"] = int(h2d)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         torch.distributed.destroy_process_group()
     return 0
@@ -409,7 +465,7 @@ def reference_cpu_arm(args, rank, world):
             "config": {"workload": f"HL: {args.surfels} surfels, {args.res}x{args.res}; one frame per step on the host cores"},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 

@@ -63,27 +63,27 @@ __device__ __forceinline__ void get_rect(float px, float py, int max_radius, int
 
 // forward.cu:20-71 (value-level parity only; no binning decision depends on the colour)
 __device__ __forceinline__ float3 sh_to_rgb(int deg, int M, float3 pos, const float* __restrict__ campos,
-                                            const float* __restrict__ sh, uint32_t& clamped) {
+                                            const float* sh, uint32_t& clamped) {
     float dx = pos.x - __ldg(campos), dy = pos.y - __ldg(campos + 1), dz = pos.z - __ldg(campos + 2);
     float len = sqrtf(dx * dx + dy * dy + dz * dz);
     float x = dx / len, y = dy / len, z = dz / len;
     float r[3];
 #pragma unroll
     for (int ch = 0; ch < 3; ch++) {
-        float v = kSH_C0 * __ldg(sh + ch);
+        float v = kSH_C0 * sh[ch];
         if (deg > 0) {
-            v = v - kSH_C1 * y * __ldg(sh + 3 + ch) + kSH_C1 * z * __ldg(sh + 6 + ch) - kSH_C1 * x * __ldg(sh + 9 + ch);
+            v = v - kSH_C1 * y * sh[3 + ch] + kSH_C1 * z * sh[6 + ch] - kSH_C1 * x * sh[9 + ch];
             if (deg > 1) {
                 float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-                v = v + kSH_C2[0] * xy * __ldg(sh + 12 + ch) + kSH_C2[1] * yz * __ldg(sh + 15 + ch) +
-                    kSH_C2[2] * (2.0f * zz - xx - yy) * __ldg(sh + 18 + ch) + kSH_C2[3] * xz * __ldg(sh + 21 + ch) +
-                    kSH_C2[4] * (xx - yy) * __ldg(sh + 24 + ch);
+                v = v + kSH_C2[0] * xy * sh[12 + ch] + kSH_C2[1] * yz * sh[15 + ch] +
+                    kSH_C2[2] * (2.0f * zz - xx - yy) * sh[18 + ch] + kSH_C2[3] * xz * sh[21 + ch] +
+                    kSH_C2[4] * (xx - yy) * sh[24 + ch];
                 if (deg > 2) {
-                    v = v + kSH_C3[0] * y * (3.0f * xx - yy) * __ldg(sh + 27 + ch) + kSH_C3[1] * xy * z * __ldg(sh + 30 + ch) +
-                        kSH_C3[2] * y * (4.0f * zz - xx - yy) * __ldg(sh + 33 + ch) +
-                        kSH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * __ldg(sh + 36 + ch) +
-                        kSH_C3[4] * x * (4.0f * zz - xx - yy) * __ldg(sh + 39 + ch) +
-                        kSH_C3[5] * z * (xx - yy) * __ldg(sh + 42 + ch) + kSH_C3[6] * x * (xx - 3.0f * yy) * __ldg(sh + 45 + ch);
+                    v = v + kSH_C3[0] * y * (3.0f * xx - yy) * sh[27 + ch] + kSH_C3[1] * xy * z * sh[30 + ch] +
+                        kSH_C3[2] * y * (4.0f * zz - xx - yy) * sh[33 + ch] +
+                        kSH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * sh[36 + ch] +
+                        kSH_C3[4] * x * (4.0f * zz - xx - yy) * sh[39 + ch] +
+                        kSH_C3[5] * z * (xx - yy) * sh[42 + ch] + kSH_C3[6] * x * (xx - 3.0f * yy) * sh[45 + ch];
                 }
             }
         }
@@ -142,7 +142,29 @@ preprocess_fwd_kernel(const CamParams c, const float* __restrict__ means3D, cons
                       int* __restrict__ radii, float4* __restrict__ srec, float* __restrict__ depths,
                       uint32_t* __restrict__ tiles_touched, uint8_t* __restrict__ clamped_out,
                       uint32_t* __restrict__ block_sums, uint32_t* __restrict__ status, int prefiltered) {
+    // The block's SH coefficients (256 x 3M floats, contiguous) are staged in shared memory with coalesced 128-bit
+    // loads; each thread then reads its own padded row (stride 3M+1: conflict-free) instead of 48 scalar loads at a
+    // 192-byte lane stride.
+    extern __shared__ float shbuf[];
     const int idx = blockIdx.x * 256 + threadIdx.x;
+    const int M3 = 3 * c.M, stride = M3 + 1;
+    if (colors_precomp == nullptr) {
+        const int base = blockIdx.x * 256;
+        const int total = min(256, c.P - base) * M3;
+        const float* gsrc = shs + (size_t)base * M3;
+        if ((M3 & 3) == 0) {
+            const float4* g4 = reinterpret_cast<const float4*>(gsrc);
+            for (int i = threadIdx.x; i < total / 4; i += 256) {
+                const float4 v = __ldg(g4 + i);
+                const int e = i * 4, r = e / M3, col = e - r * M3;
+                float* d = shbuf + r * stride + col;
+                d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+            }
+        } else {
+            for (int i = threadIdx.x; i < total; i += 256) { const int r = i / M3; shbuf[r * stride + (i - r * M3)] = __ldg(gsrc + i); }
+        }
+        __syncthreads();
+    }
     uint32_t touched = 0;
     int radius_i = 0;
     if (idx < c.P) {
@@ -207,7 +229,7 @@ preprocess_fwd_kernel(const CamParams c, const float* __restrict__ means3D, cons
                         uint32_t cl = 0;
                         float3 rgb;
                         if (colors_precomp == nullptr) {
-                            rgb = sh_to_rgb(c.D, c.M, make_float3(px, py, pz), c.campos, shs + (size_t)idx * c.M * 3, cl);
+                            rgb = sh_to_rgb(c.D, c.M, make_float3(px, py, pz), c.campos, shbuf + threadIdx.x * stride, cl);
                         } else {
                             rgb = make_float3(__ldg(colors_precomp + 3 * (size_t)idx), __ldg(colors_precomp + 3 * (size_t)idx + 1),
                                               __ldg(colors_precomp + 3 * (size_t)idx + 2));
@@ -357,8 +379,15 @@ __global__ void mark_visible_kernel(int P, const float* __restrict__ means3D, co
 
 cudaError_t launch_preprocess_fwd(const FwdArgs& a) {
     const int nb = a.gl.nblocks;
+    const size_t smem = a.colors_precomp ? 0 : (size_t)256 * (3 * a.cam.M + 1) * sizeof(float);
+    static size_t smem_set = 0;     // opt in to > 48 KB dynamic shared memory once (not a stream operation)
+    if (smem > 48 * 1024 && smem > smem_set) {
+        cudaError_t e = cudaFuncSetAttribute(preprocess_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        smem_set = smem;
+    }
     ProfileScope ps("preprocess_fwd", a.stream);
-    preprocess_fwd_kernel<<<nb, 256, 0, a.stream>>>(
+    preprocess_fwd_kernel<<<nb, 256, smem, a.stream>>>(
         a.cam, a.means3D, a.shs, a.colors_precomp, a.opacities, (const float2*)a.scales, (const float4*)a.rotations,
         a.radii, (float4*)(a.geom + a.gl.surfel_rec), (float*)(a.geom + a.gl.depths),
         (uint32_t*)(a.geom + a.gl.tiles_touched), (uint8_t*)(a.geom + a.gl.clamped),

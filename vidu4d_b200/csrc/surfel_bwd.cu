@@ -31,17 +31,75 @@ __device__ __forceinline__ V3 wtmul(const float* m, V3 v) {     // W^T * v
     return {m[0] * v.x + m[1] * v.y + m[2] * v.z, m[4] * v.x + m[5] * v.y + m[6] * v.z, m[8] * v.x + m[9] * v.y + m[10] * v.z};
 }
 
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ void
+surfel_bwd_body(const CamParams& c, const int idx, const int M, float* osh, const float* __restrict__ means3D, const bool has_sh,
+                const float2* __restrict__ scales, const float4* __restrict__ rotations, const int* __restrict__ radii,
+                const float4* __restrict__ srec, const uint8_t* __restrict__ clamped, const float4* __restrict__ sgrad,
+                float* __restrict__ dL_dmeans2D, float* __restrict__ dL_dcolors, float* __restrict__ dL_dopacity,
+                float* __restrict__ dL_dmeans3D, float* __restrict__ dL_dtransMat,
+                float2* __restrict__ dL_dscales, float4* __restrict__ dL_drotations);
+
+// Block = 128 surfels.  The block's SH coefficients (128 x 3M floats, contiguous in HBM) are pulled into shared
+// memory with coalesced 128-bit loads, each thread works on its own padded row (stride 3M+1: conflict-free),
+// overwrites it with dL/dSH, and the block streams the rows back out coalesced -- instead of 48 scalar loads and
+// 48 scalar stores per thread at a 192-byte lane stride (r1a: 118 us for 175 MB).
+constexpr int SB = 128;
+
+__global__ void __launch_bounds__(SB)
 surfel_bwd_kernel(const CamParams c, const float* __restrict__ means3D, const float* __restrict__ shs,
                   const float2* __restrict__ scales, const float4* __restrict__ rotations, const int* __restrict__ radii,
                   const float4* __restrict__ srec, const uint8_t* __restrict__ clamped, const float4* __restrict__ sgrad,
                   float* __restrict__ dL_dmeans2D, float* __restrict__ dL_dcolors, float* __restrict__ dL_dopacity,
                   float* __restrict__ dL_dmeans3D, float* __restrict__ dL_dtransMat, float* __restrict__ dL_dsh,
                   float2* __restrict__ dL_dscales, float4* __restrict__ dL_drotations) {
-    const int idx = blockIdx.x * 256 + threadIdx.x;
-    if (idx >= c.P) return;
-    const int M = c.M;
-    float* osh = dL_dsh + (size_t)idx * M * 3;
+    extern __shared__ float shbuf[];
+    const int M = c.M, M3 = 3 * c.M, stride = M3 + 1;
+    const int idx = blockIdx.x * SB + threadIdx.x;
+    const int base = blockIdx.x * SB;
+    const int nrows = min(SB, c.P - base);
+    if (shs != nullptr) {
+        const float* gsrc = shs + (size_t)base * M3;
+        const int total = nrows * M3;
+        if ((M3 & 3) == 0) {
+            const float4* g4 = reinterpret_cast<const float4*>(gsrc);
+            for (int i = threadIdx.x; i < total / 4; i += SB) {
+                const float4 v = __ldg(g4 + i);
+                const int e = i * 4, r = e / M3, col = e - r * M3;     // 4 | M3 => the four stay in one row
+                float* d = shbuf + r * stride + col;
+                d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+            }
+        } else {
+            for (int i = threadIdx.x; i < total; i += SB) { const int r = i / M3; shbuf[r * stride + (i - r * M3)] = __ldg(gsrc + i); }
+        }
+    }
+    __syncthreads();
+    float* osh = shbuf + threadIdx.x * stride;      // this thread's row: SH in, dL/dSH out
+    if (idx < c.P) surfel_bwd_body(c, idx, M, osh, means3D, shs != nullptr, scales, rotations, radii, srec, clamped, sgrad,
+                                   dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dtransMat, dL_dscales, dL_drotations);
+    __syncthreads();
+    if (shs != nullptr) {
+        float* gdst = dL_dsh + (size_t)base * M3;
+        const int total = nrows * M3;
+        if ((M3 & 3) == 0) {
+            float4* g4 = reinterpret_cast<float4*>(gdst);
+            for (int i = threadIdx.x; i < total / 4; i += SB) {
+                const int e = i * 4, r = e / M3, col = e - r * M3;
+                const float* d = shbuf + r * stride + col;
+                g4[i] = make_float4(d[0], d[1], d[2], d[3]);
+            }
+        } else {
+            for (int i = threadIdx.x; i < total; i += SB) { const int r = i / M3; gdst[i] = shbuf[r * stride + (i - r * M3)]; }
+        }
+    }
+}
+
+__device__ __forceinline__ void
+surfel_bwd_body(const CamParams& c, const int idx, const int M, float* osh, const float* __restrict__ means3D, const bool has_sh,
+                const float2* __restrict__ scales, const float4* __restrict__ rotations, const int* __restrict__ radii,
+                const float4* __restrict__ srec, const uint8_t* __restrict__ clamped, const float4* __restrict__ sgrad,
+                float* __restrict__ dL_dmeans2D, float* __restrict__ dL_dcolors, float* __restrict__ dL_dopacity,
+                float* __restrict__ dL_dmeans3D, float* __restrict__ dL_dtransMat,
+                float2* __restrict__ dL_dscales, float4* __restrict__ dL_drotations) {
     if (!(radii[idx] > 0)) {
         // invisible: every gradient is zero (the reference leaves its zero-filled tensors untouched)
 #pragma unroll
@@ -135,8 +193,7 @@ surfel_bwd_kernel(const CamParams c, const float* __restrict__ means3D, const fl
     float dmean[3] = {dpw.x, dpw.y, dpw.z};
 
     // ---- SH vjp (backward.cu:20-139) ----
-    if (shs != nullptr) {
-        const float* sh = shs + (size_t)idx * M * 3;
+    if (has_sh) {
         const int deg = c.D;
         const float dox = p.x - __ldg(c.campos), doy = p.y - __ldg(c.campos + 1), doz = p.z - __ldg(c.campos + 2);
         const float len = sqrtf(dox * dox + doy * doy + doz * doz);
@@ -146,22 +203,11 @@ surfel_bwd_kernel(const CamParams c, const float* __restrict__ means3D, const fl
 #pragma unroll
         for (int ch = 0; ch < 3; ch++) dRGB[ch] = (cl >> ch) & 1u ? 0.f : dcol[ch];
         float ddx = 0.f, ddy = 0.f, ddz = 0.f;   // dL/ddir accumulated over channels
-#define SH(k, ch) __ldg(sh + 3 * (k) + (ch))
+#define SH(k, ch) osh[3 * (k) + (ch)]
 #define SETSH(k, wgt) { const float w_ = (wgt); osh[3 * (k)] = w_ * dRGB[0]; osh[3 * (k) + 1] = w_ * dRGB[1]; osh[3 * (k) + 2] = w_ * dRGB[2]; }
-        SETSH(0, kSH_C0);
+        const float xx = dx * dx, yy = dy * dy, zz = dz * dz, xy = dx * dy, yz = dy * dz, xz = dx * dz;
+        // (1) gradient w.r.t. the view direction: reads the SH row, so it runs BEFORE the row is overwritten in place
         if (deg > 0) {
-            SETSH(1, -kSH_C1 * dy); SETSH(2, kSH_C1 * dz); SETSH(3, -kSH_C1 * dx);
-            const float xx = dx * dx, yy = dy * dy, zz = dz * dz, xy = dx * dy, yz = dy * dz, xz = dx * dz;
-            if (deg > 1) {
-                SETSH(4, kSH_C2[0] * xy); SETSH(5, kSH_C2[1] * yz); SETSH(6, kSH_C2[2] * (2.f * zz - xx - yy));
-                SETSH(7, kSH_C2[3] * xz); SETSH(8, kSH_C2[4] * (xx - yy));
-                if (deg > 2) {
-                    SETSH(9, kSH_C3[0] * dy * (3.f * xx - yy)); SETSH(10, kSH_C3[1] * xy * dz);
-                    SETSH(11, kSH_C3[2] * dy * (4.f * zz - xx - yy)); SETSH(12, kSH_C3[3] * dz * (2.f * zz - 3.f * xx - 3.f * yy));
-                    SETSH(13, kSH_C3[4] * dx * (4.f * zz - xx - yy)); SETSH(14, kSH_C3[5] * dz * (xx - yy));
-                    SETSH(15, kSH_C3[6] * dx * (xx - 3.f * yy));
-                }
-            }
 #pragma unroll
             for (int ch = 0; ch < 3; ch++) {
                 float gx = -kSH_C1 * SH(3, ch), gy = -kSH_C1 * SH(1, ch), gz = kSH_C1 * SH(2, ch);
@@ -184,6 +230,21 @@ surfel_bwd_kernel(const CamParams c, const float* __restrict__ means3D, const fl
                 ddx += gx * dRGB[ch]; ddy += gy * dRGB[ch]; ddz += gz * dRGB[ch];
             }
         }
+        // (2) dL/dSH, written over the row
+        SETSH(0, kSH_C0);
+        if (deg > 0) {
+            SETSH(1, -kSH_C1 * dy); SETSH(2, kSH_C1 * dz); SETSH(3, -kSH_C1 * dx);
+            if (deg > 1) {
+                SETSH(4, kSH_C2[0] * xy); SETSH(5, kSH_C2[1] * yz); SETSH(6, kSH_C2[2] * (2.f * zz - xx - yy));
+                SETSH(7, kSH_C2[3] * xz); SETSH(8, kSH_C2[4] * (xx - yy));
+                if (deg > 2) {
+                    SETSH(9, kSH_C3[0] * dy * (3.f * xx - yy)); SETSH(10, kSH_C3[1] * xy * dz);
+                    SETSH(11, kSH_C3[2] * dy * (4.f * zz - xx - yy)); SETSH(12, kSH_C3[3] * dz * (2.f * zz - 3.f * xx - 3.f * yy));
+                    SETSH(13, kSH_C3[4] * dx * (4.f * zz - xx - yy)); SETSH(14, kSH_C3[5] * dz * (xx - yy));
+                    SETSH(15, kSH_C3[6] * dx * (xx - 3.f * yy));
+                }
+            }
+        }
         // coefficients above the active degree receive no gradient
         const int used = (deg + 1) * (deg + 1);
         for (int k = used; k < M; k++) { osh[3 * k] = 0.f; osh[3 * k + 1] = 0.f; osh[3 * k + 2] = 0.f; }
@@ -204,9 +265,16 @@ surfel_bwd_kernel(const CamParams c, const float* __restrict__ means3D, const fl
 }  // namespace
 
 cudaError_t launch_surfel_bwd(const BwdArgs& a) {
-    const int nb = a.gl.nblocks;
+    const int nb = (a.cam.P + SB - 1) / SB;
+    const size_t smem = (size_t)SB * (3 * a.cam.M + 1) * sizeof(float);
+    static size_t smem_set = 0;     // opt in to > 48 KB dynamic shared memory once (not a stream operation)
+    if (smem > 48 * 1024 && smem > smem_set) {
+        cudaError_t e = cudaFuncSetAttribute(surfel_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        smem_set = smem;
+    }
     ProfileScope ps("surfel_bwd", a.stream);
-    surfel_bwd_kernel<<<nb, 256, 0, a.stream>>>(
+    surfel_bwd_kernel<<<nb, SB, smem, a.stream>>>(
         a.cam, a.means3D, a.shs, (const float2*)a.scales, (const float4*)a.rotations, a.radii,
         (const float4*)(a.geom + a.gl.surfel_rec), (const uint8_t*)(a.geom + a.gl.clamped),
         (const float4*)(a.geom + a.gl.sgrad), a.dL_dmeans2D, a.dL_dcolors, a.dL_dopacity, a.dL_dmeans3D,

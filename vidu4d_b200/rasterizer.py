@@ -32,7 +32,9 @@ from . import _capi
 _CAP_ALIGN = 256           # capacities are multiples of this so that bytes -> capacity is invertible
 _cap_hint: dict = {}       # (device index, W, H) -> last seen num_rendered
 _sync_mode = True          # True: read num_rendered back after every forward (like the reference)
-_pending: list = []        # nosync mode: (pinned host word, event, key, capacity) awaiting check_overflow()
+_pending: list = []        # nosync mode: (pinned host word, key, capacity) awaiting check_overflow()
+_host_pool: list = []      # pinned uint32[2] words, pre-allocated so that a forward never allocates pinned memory
+_host_next = 0             #   (cudaHostAlloc is illegal during CUDA-graph capture)
 
 
 def set_sync_mode(flag: bool):
@@ -77,17 +79,38 @@ def _capacity_from_bytes(nbytes: int) -> int:
     return cap
 
 
-def check_overflow():
+def reserve_host_slots(n: int):
+    """Pre-allocate pinned status words for the next `n` nosync forwards (needed before CUDA-graph capture)."""
+    while len(_host_pool) - _host_next < n:
+        _host_pool.append(torch.zeros((2,), dtype=torch.int32).pin_memory())
+
+
+def _host_slot():
+    global _host_next
+    if _host_next >= len(_host_pool):
+        _host_pool.append(torch.zeros((2,), dtype=torch.int32).pin_memory())
+    h = _host_pool[_host_next]
+    _host_next += 1
+    return h
+
+
+def check_overflow(keep: bool = False):
     """nosync mode: synchronise once, verify that no forward since the last call overflowed its instance
-    buffer, and refresh the capacity hints.  Raises SurfelRasterError if a frame was dropped."""
+    buffer, and refresh the capacity hints.  Raises SurfelRasterError if a frame was dropped.
+    keep=True leaves the watch list in place (a captured CUDA graph rewrites the same status words on every
+    replay: call check_overflow(keep=True) after each replay)."""
+    global _host_next
     bad = None
-    for host, ev, key, cap in _pending:
-        ev.synchronize()
+    if _pending:
+        torch.cuda.synchronize()
+    for host, key, cap in _pending:
         r, status = int(host[0]), int(host[1])
         _cap_hint[key] = max(_cap_hint.get(key, 0), r)
         if status & _capi.SR_STATUS_OVERFLOW:
             bad = (r, cap)
-    _pending.clear()
+    if not keep:
+        _pending.clear()
+        _host_next = 0
     if bad:
         raise _capi.SurfelRasterError(
             f"instance buffer overflow in nosync mode: num_rendered={bad[0]} > capacity={bad[1]}; "
@@ -157,7 +180,8 @@ class _CNamespace:
             cap = _pick_capacity(key, P)
             while True:
                 binning = torch.empty((lib.sr_binning_bytes(cap, W, H),), dtype=torch.uint8, device=dev)
-                host = torch.empty((2,), dtype=torch.int32, pin_memory=True)
+                nosync = (not _sync_mode) and key in _cap_hint
+                host = _host_slot() if nosync else torch.empty((2,), dtype=torch.int32, pin_memory=True)
                 rc = lib.sr_forward(
                     C.byref(fr), _ptr(background), _ptr(means3D), _ptr(sh), _ptr(colors), _ptr(opacity),
                     _ptr(scales), _ptr(rotations), _ptr(viewmatrix), _ptr(projmatrix), _ptr(campos),
@@ -165,10 +189,8 @@ class _CNamespace:
                     binning.data_ptr(), img.data_ptr(), cap, nr_dev.data_ptr(), host.data_ptr(),
                     stream.cuda_stream)
                 _capi.check(rc, "sr_forward")
-                if not _sync_mode and key in _cap_hint:
-                    ev = torch.cuda.Event()
-                    ev.record(stream)
-                    _pending.append((host, ev, key, cap))
+                if nosync:
+                    _pending.append((host, key, cap))
                     num_rendered = -1
                     break
                 stream.synchronize()

@@ -105,8 +105,8 @@ _dir_cache: dict = {}
 def _rays(view, device):
     """rays_d (H*W,3) and rays_o (3,) of depths_to_points (point_utils.py:9-21).  The camera-space pixel
     directions (pixel grid times K^-1) are cached per (W,H,fov); the per-frame camera-to-world factor uses
-    inv_ex (no error check => no host synchronisation), so the reference's per-call torch.tensor(...).cuda(),
-    .inverse() and math.tan(cuda tensor) syncs are gone."""
+    the adjugate formula, so the reference's per-call torch.tensor(...).cuda(), .inverse() and math.tan(cuda
+    tensor) syncs are gone."""
     W, H = int(view.image_width), int(view.image_height)
     tx, ty = _tan_half(view.FoVx), _tan_half(view.FoVy)
     key = (W, H, tx, ty, str(device))
@@ -120,9 +120,14 @@ def _rays(view, device):
         if len(_dir_cache) > 16:
             _dir_cache.clear()
         _dir_cache[key] = dirs
-    c2w = torch.linalg.inv_ex(view.world_view_transform.T, check_errors=False).inverse
-    rays_d = dirs @ c2w[:3, :3].T
-    rays_o = c2w[:3, 3]
+    # camera-to-world of the affine view matrix by the adjugate formula: plain elementwise torch ops -- no host
+    # synchronisation, no solver workspace, capturable in a CUDA graph (the reference calls .inverse() per frame)
+    w2c = view.world_view_transform.T
+    A, t = w2c[:3, :3], w2c[:3, 3]
+    c0 = torch.linalg.cross(A[1], A[2]); c1 = torch.linalg.cross(A[2], A[0]); c2 = torch.linalg.cross(A[0], A[1])
+    Ainv = torch.stack([c0, c1, c2], dim=1) / (A[0] * c0).sum()
+    rays_d = dirs @ Ainv.T
+    rays_o = -(Ainv @ t)
     return rays_d, rays_o
 
 

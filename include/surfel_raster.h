@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define SR_ABI_VERSION 1
+#define SR_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define SR_API __attribute__((visibility("default")))
@@ -57,6 +57,14 @@ extern "C" {
 /* bits of the device/host status word written by sr_forward() */
 #define SR_STATUS_OK        0u
 #define SR_STATUS_OVERFLOW  1u   /* num_rendered > capacity: nothing was binned or composited */
+#define SR_STATUS_PREFILTER 4u   /* prefiltered was set but a surfel was culled (the reference __trap()s) */
+#define SR_STATUS_SORT_CAP  8u   /* SR_FLAG_LOCAL_SORT: a tile holds more instances than the shared-memory sort takes;
+                                    nothing was composited -- call again without the flag */
+
+/* sr_frame.flags */
+#define SR_FLAG_LOCAL_SORT  1u   /* bin by tile with atomics, sort each tile's (depth, id) list in shared memory
+                                    (same order as the global stable radix sort: ties are broken by surfel id, which is
+                                    the emission order); falls back via SR_STATUS_SORT_CAP */
 
 /* One frame's static description (GaussianRasterizationSettings,
  * RAST/diff_surfel_rasterization/__init__.py:158-170, plus P/M). */
@@ -69,6 +77,7 @@ typedef struct sr_frame {
     float   scale_modifier;  /* accepted and ignored, exactly like the reference (forward.cu:95) */
     int32_t prefiltered;     /* if set, a culled surfel is an error in the reference (__trap); we report it via status bit 2 */
     int32_t debug;           /* if set, synchronise + check after every launch (auxiliary.h:271-278) */
+    uint32_t flags;          /* SR_FLAG_* */
 } sr_frame;
 
 /* ---- buffer sizing (replaces required<GeometryState/ImageState/BinningState>, rasterizer_impl.h:66-72) */

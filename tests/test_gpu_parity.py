@@ -179,7 +179,7 @@ def test_full_size_structure(headline):
     inp, r = headline
     R = r["num_rendered"]
     keys = r["keys"]
-    assert R == int(r["tiles_touched"].sum().item()) == int(r["point_offsets"][-1].item())
+    assert R == int(r["tiles_touched"].sum().item())
     assert bool((keys[1:] >= keys[:-1]).all()), "sorted by (tile, depth)"
     rg = r["ranges"].long()
     nz = rg[(rg[:, 1] - rg[:, 0]) > 0]
@@ -320,3 +320,39 @@ def test_non_default_stream_and_noncontiguous_inputs(dev):
     out = R._C.rasterize_gaussians(t["bg"], big[:, ::2], e, t["opacities"], t["scales"], t["rotations"], 1.0, e, t["viewmatrix"],
                                    t["projmatrix"], 0.5, 0.5, 96, 96, t["shs"], 3, t["campos"], False, False)
     assert torch.equal(out[1], base["color"])
+
+
+def test_local_and_global_sort_paths_agree_and_fallback(dev):
+    """The tile-local sort (default) and the global onesweep radix sort produce the same sorted instance list; a
+    tile with more instances than the shared-memory sort takes makes the library fall back to the global path."""
+    from oracle import surfel_oracle as so
+    from tests.golden.make_golden import build_case
+    from vidu4d_b200 import rasterizer as R
+    inp = build_case(30000, 256, 192, 71, rigid=True)
+    key = (dev.index, 256, 192)
+    R._sort_global.discard(key)
+    a = _run_ours(inp, dev)
+    assert key not in R._sort_global
+    R._sort_global.add(key)
+    try:
+        b = _run_ours(inp, dev)
+    finally:
+        R._sort_global.discard(key)
+    assert a["num_rendered"] == b["num_rendered"]
+    for k in ("keys", "point_list", "ranges", "color", "allmap", "n_contrib"):
+        assert torch.equal(a[k], b[k]), k
+    for k in GRADS:
+        assert float((a["grads"][k] - b["grads"][k]).abs().max()) <= 1e-5 * float(b["grads"][k].abs().max() + 1e-30), k
+    # 50 K surfels on a 32x32 image: 4 tiles, each far beyond SR_LOCAL_SORT_CAP = 8192 instances
+    inp = build_case(50000, 32, 32, 72)
+    key = (dev.index, 32, 32)
+    R._sort_global.discard(key)
+    r = _run_ours(inp, dev, with_grads=False)
+    assert key in R._sort_global, "the library should have switched this image size to the global sort"
+    st = so.forward(inp["means3D"], inp["opacities"], inp["scales"], inp["rotations"], shs=inp["shs"], sh_degree=3, W=32, H=32,
+                    tanfovx=0.5, tanfovy=0.5, bg=inp["bg"], viewmatrix=inp["viewmatrix"], projmatrix=inp["projmatrix"],
+                    campos=inp["campos"])
+    assert r["num_rendered"] == st.num_rendered and int(_np(r["ranges"]).max()) > 8192
+    np.testing.assert_array_equal(_np(r["point_list"]).astype(np.uint32), st.point_list)
+    _assert_close_robust(_np(r["color"]), st.color, TOL, "color")
+    R._sort_global.discard(key)

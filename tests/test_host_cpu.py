@@ -58,12 +58,12 @@ def test_argument_validation_without_gpu(built):
     from vidu4d_b200 import _capi
     lib = _capi.load()
     nul = [None] * 16 + [0] + [None] * 3      # 16 pointers, capacity, 3 pointers
-    fr = _capi.SrFrame(10, 3, 16, -5, 64, 0.5, 0.5, 1.0, 0, 0)
+    fr = _capi.SrFrame(10, 3, 16, -5, 64, 0.5, 0.5, 1.0, 0, 0, 0)
     rc = lib.sr_forward(C.byref(fr), *nul)
     assert rc == -1 and b"image size" in lib.sr_last_error()
-    fr = _capi.SrFrame(10, 5, 16, 64, 64, 0.5, 0.5, 1.0, 0, 0)
+    fr = _capi.SrFrame(10, 5, 16, 64, 64, 0.5, 0.5, 1.0, 0, 0, 0)
     assert lib.sr_forward(C.byref(fr), *nul) == -1 and b"sh_degree" in lib.sr_last_error()
-    fr = _capi.SrFrame(10, 3, 4, 64, 64, 0.5, 0.5, 1.0, 0, 0)
+    fr = _capi.SrFrame(10, 3, 4, 64, 64, 0.5, 0.5, 1.0, 0, 0, 0)
     assert lib.sr_forward(C.byref(fr), *nul) == -1 and b"coefficients" in lib.sr_last_error()
     assert lib.sr_mark_visible(-1, None, None, None, None, None) == -1
 

@@ -11,9 +11,11 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libsurfel_raster.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 SR_STATUS_OVERFLOW = 1
 SR_STATUS_PREFILTER = 4
+SR_STATUS_SORT_CAP = 8
+SR_FLAG_LOCAL_SORT = 1
 
 SYMBOLS = (
     "sr_geom_bytes", "sr_image_bytes", "sr_binning_bytes", "sr_forward", "sr_backward",
@@ -27,7 +29,7 @@ class SrFrame(C.Structure):
         ("P", C.c_int32), ("sh_degree", C.c_int32), ("sh_coeffs", C.c_int32),
         ("width", C.c_int32), ("height", C.c_int32),
         ("tan_fovx", C.c_float), ("tan_fovy", C.c_float), ("scale_modifier", C.c_float),
-        ("prefiltered", C.c_int32), ("debug", C.c_int32),
+        ("prefiltered", C.c_int32), ("debug", C.c_int32), ("flags", C.c_uint32),
     ]
 
 

@@ -176,14 +176,25 @@ int sr_forward(const sr_frame* f, const float* background, const float* means3D,
     a.key_bits = 32 + (int)sr_higher_msb((uint32_t)a.il.tiles);
     a.stream = stream; a.debug = debug;
 
-    // one memset clears sort control words, digit histograms and look-back status; one clears ranges+tile_last
-    CK(cudaMemsetAsync(a.bin + a.bl.sort_ctl, 0, a.bl.total - a.bl.sort_ctl, stream), "memset(sort state)");
-    CK(cudaMemsetAsync(a.img + a.il.ranges, 0, a.il.total - a.il.ranges, stream), "memset(ranges)");
-    CK(launch_preprocess_fwd(a), "preprocess_fwd"); DBG("preprocess_fwd");
-    CK(launch_scan_emit(a), "scan/emit_keys"); DBG("scan/emit_keys");
-    CK(launch_sort(a), "sort"); DBG("sort");
-    CK(launch_ranges_gather(a), "ranges_gather"); DBG("ranges_gather");
-    CK(launch_tile_order(a), "tile_order"); DBG("tile_order");
+    a.local_sort = (f->flags & SR_FLAG_LOCAL_SORT) ? 1 : 0;
+    CK(cudaMemsetAsync(a.img + a.il.ranges, 0, a.il.total - a.il.ranges, stream), "memset(tile state)");
+    if (a.local_sort) {
+        // tile-local path (tile_sort.cu): per-tile counts -> ranges -> scatter -> shared-memory sort + record stream
+        CK(cudaMemsetAsync(a.bin + a.bl.sort_ctl, 0, SR_CTL_WORDS * 4, stream), "memset(sort ctl)");
+        // the sorted arrays are the "pong" halves: sort_ctl[SR_CTL_SORTED_SEL] = 1 (little-endian low byte)
+        CK(cudaMemsetAsync(a.bin + a.bl.sort_ctl + 4 * SR_CTL_SORTED_SEL, 1, 1, stream), "set(sorted_sel)");
+        CK(launch_preprocess_fwd(a), "preprocess_fwd"); DBG("preprocess_fwd");
+        CK(launch_tile_scan_emit(a), "tile_scan/emit_local"); DBG("tile_scan/emit_local");
+        CK(launch_tile_sort_gather(a), "tile_sort_gather"); DBG("tile_sort_gather");
+    } else {
+        // global path (sort.cu): one memset clears sort control words, digit histograms and look-back status
+        CK(cudaMemsetAsync(a.bin + a.bl.sort_ctl, 0, a.bl.total - a.bl.sort_ctl, stream), "memset(sort state)");
+        CK(launch_preprocess_fwd(a), "preprocess_fwd"); DBG("preprocess_fwd");
+        CK(launch_scan_emit(a), "scan/emit_keys"); DBG("scan/emit_keys");
+        CK(launch_sort(a), "sort"); DBG("sort");
+        CK(launch_ranges_gather(a), "ranges_gather"); DBG("ranges_gather");
+        CK(launch_tile_order(a), "tile_order"); DBG("tile_order");
+    }
     CK(launch_composite_fwd(a), "composite_fwd"); DBG("composite_fwd");
     if (num_rendered_host)
         CK(cudaMemcpyAsync(num_rendered_host, num_rendered_dev, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream), "copy(num_rendered)");

@@ -40,6 +40,8 @@
 #define SR_G_COLOR 12
 #define SR_G_NORMAL 15
 
+#define SR_LOCAL_SORT_CAP 8192   // max instances of one tile the tile-local sort holds in shared memory
+#define SR_STATUS_SORT_CAP 8u     // status bit: a tile exceeded it -- re-run with the global onesweep path
 #define SR_SORT_MAX_PASSES 8
 #define SR_SORT_RADIX_BITS 8
 #define SR_SORT_BINS 256
@@ -62,7 +64,7 @@ struct GeomLayout {
     int nblocks;
 };
 struct ImageLayout {
-    size_t final_T, n_contrib, ranges, tile_last, tile_order, total;
+    size_t final_T, n_contrib, ranges, tile_last, tile_order, tile_count, tile_cursor, total;
     int tiles_x, tiles_y, tiles;
 };
 struct BinLayout {
@@ -95,6 +97,8 @@ static inline __host__ __device__ ImageLayout image_layout(int W, int H) {
     L.ranges = o;    o = sr_align_up(o + (size_t)L.tiles * 8);
     L.tile_last = o; o = sr_align_up(o + (size_t)L.tiles * 8 * 4);   // per 8x4 sub-tile: deepest contributor
     L.tile_order = o; o = sr_align_up(o + (size_t)L.tiles * 4);       // tiles, longest instance list first
+    L.tile_count = o; o = sr_align_up(o + (size_t)L.tiles * 4);       // tile-local sort: instances per tile
+    L.tile_cursor = o; o = sr_align_up(o + (size_t)L.tiles * 4);      // tile-local sort: scatter cursors
     L.total = o;
     return L;
 }
@@ -145,6 +149,7 @@ struct FwdArgs {
     GeomLayout gl; BinLayout bl; ImageLayout il;
     uint32_t* num_rendered_dev;   // [0]=R, [1]=status
     int prefiltered;
+    int local_sort;               // 1: tile-local sort path (tile_sort.cu), 0: global onesweep (sort.cu)
     int key_bits;                 // 32 + getHigherMsb(tiles)
     cudaStream_t stream;
     bool debug;
@@ -167,6 +172,8 @@ cudaError_t launch_scan_emit(const FwdArgs& a);           // preprocess.cu
 cudaError_t launch_sort(const FwdArgs& a);                // sort.cu
 cudaError_t launch_ranges_gather(const FwdArgs& a);       // sort.cu
 cudaError_t launch_tile_order(const FwdArgs& a);          // sort.cu
+cudaError_t launch_tile_scan_emit(const FwdArgs& a);      // tile_sort.cu
+cudaError_t launch_tile_sort_gather(const FwdArgs& a);    // tile_sort.cu
 cudaError_t launch_composite_fwd(const FwdArgs& a);       // composite_fwd.cu
 cudaError_t launch_composite_bwd(const BwdArgs& a);       // composite_bwd.cu
 cudaError_t launch_surfel_bwd(const BwdArgs& a);          // surfel_bwd.cu

@@ -164,7 +164,10 @@ composite_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
                     if (!(c_d < 0.2f) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f)) {
                         contrib = true;
                         const float4 r3 = S[jj * REC4 + 3], r4 = S[jj * REC4 + 4];
-                        T = T / (1.f - alpha);
+                        // one approximate reciprocal of (1 - alpha) serves the transmittance recurrence and the
+                        // background term (the reference divides twice, IEEE; the difference is ~1 ulp per step)
+                        const float r1ma = rcp_approx(1.f - alpha);
+                        T = T * r1ma;
                         const float aT = alpha * T;
                         float dL_dalpha = 0.f;
                         // colour
@@ -176,8 +179,8 @@ composite_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
                         v[10] = aT * dpix0; v[11] = aT * dpix1; v[12] = aT * dpix2;
                         // distortion / median
                         float dL_dz = 0.f, dL_dweight = 0.f;
-                        const float m_d = map_depth(c_d);
-                        const float dmd_dd = map_depth_grad(c_d);
+                        float m_d, dmd_dd;
+                        map_depth_vg(c_d, m_d, dmd_dd);
                         if (pos == median_contributor - 1) { dL_dz += dL_dmedian_depth; dL_dweight += dL_dmax_dweight; }
                         dL_dweight += (final_D2 + m_d * m_d * final_A - 2.f * m_d * final_D) * dL_dreg;
                         dL_dalpha += dL_dweight - last_dL_dT;
@@ -200,13 +203,13 @@ composite_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
 
                         dL_dalpha *= T;
                         last_alpha = alpha;
-                        dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
+                        dL_dalpha += (-T_final * r1ma) * bg_dot_dpixel;
                         const float dL_dG = r2.w * dL_dalpha;
                         dL_dz += aT * dL_ddepth;
                         if (rho3d <= rho2d) {
                             const float dL_dsx = dL_dG * -G * sx + dL_dz * r1.z;
                             const float dL_dsy = dL_dG * -G * sy + dL_dz * r1.w;
-                            const float rpz = 1.0f / pz;
+                            const float rpz = rcp_approx(pz);
                             const float dpx = dL_dsx * rpz, dpy = dL_dsy * rpz, dpz = -(dpx * sx + dpy * sy);
                             // dL_dk = l x dL_dp ; dL_dl = dL_dp x k
                             const float dkx = ly_ * dpz - lz_ * dpy, dky = lz_ * dpx - lx_ * dpz, dkz = lx_ * dpy - ly_ * dpx;
@@ -232,12 +235,12 @@ composite_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
                 butterfly16(v, lane);
                 if ((lane & 1) == 0) atomicAdd(g + comp_slot(lane >> 1), v[0]);
                 if (__any_sync(0xffffffffu, lowpass)) {
+                    // 2-value halving butterfly: lanes 0..15 end with sum(m2x), lanes 16..31 with sum(m2y)
+                    const bool hi = lane & 16;
+                    float w = (hi ? m2y : m2x) + __shfl_xor_sync(0xffffffffu, hi ? m2x : m2y, 16);
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        m2x += __shfl_xor_sync(0xffffffffu, m2x, o);
-                        m2y += __shfl_xor_sync(0xffffffffu, m2y, o);
-                    }
-                    if (lane == 0) { atomicAdd(g + SR_G_M2D, m2x); atomicAdd(g + SR_G_M2D + 1, m2y); }
+                    for (int o = 8; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+                    if ((lane & 15) == 0) atomicAdd(g + SR_G_M2D + (lane >> 4), w);
                 }
             }
         }

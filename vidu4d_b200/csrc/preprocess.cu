@@ -141,7 +141,8 @@ preprocess_fwd_kernel(const CamParams c, const float* __restrict__ means3D, cons
                       const float2* __restrict__ scales, const float4* __restrict__ rotations,
                       int* __restrict__ radii, float4* __restrict__ srec, float* __restrict__ depths,
                       uint32_t* __restrict__ tiles_touched, uint8_t* __restrict__ clamped_out,
-                      uint32_t* __restrict__ block_sums, uint32_t* __restrict__ status, int prefiltered) {
+                      uint32_t* __restrict__ block_sums, uint32_t* __restrict__ status, int prefiltered,
+                      uint32_t* __restrict__ tile_count /* tile-local sort: per-tile instance counters, else nullptr */) {
     // The block's SH coefficients (256 x 3M floats, contiguous) are staged in shared memory with coalesced 128-bit
     // loads; each thread then reads its own padded row (stride 3M+1: conflict-free) instead of 48 scalar loads at a
     // 192-byte lane stride.
@@ -247,6 +248,9 @@ preprocess_fwd_kernel(const CamParams c, const float* __restrict__ means3D, cons
                         clamped_out[idx] = (uint8_t)cl;
                         radius_i = ri;
                         touched = area;
+                        if (tile_count != nullptr)
+                            for (uint32_t y = rmin.y; y < rmax.y; y++)
+                                for (uint32_t x = rmin.x; x < rmax.x; x++) atomicAdd(&tile_count[y * (uint32_t)c.tiles_x + x], 1u);
                     }
                 }
             }
@@ -391,7 +395,8 @@ cudaError_t launch_preprocess_fwd(const FwdArgs& a) {
         a.cam, a.means3D, a.shs, a.colors_precomp, a.opacities, (const float2*)a.scales, (const float4*)a.rotations,
         a.radii, (float4*)(a.geom + a.gl.surfel_rec), (float*)(a.geom + a.gl.depths),
         (uint32_t*)(a.geom + a.gl.tiles_touched), (uint8_t*)(a.geom + a.gl.clamped),
-        (uint32_t*)(a.geom + a.gl.block_sums), a.num_rendered_dev + 1, a.prefiltered);
+        (uint32_t*)(a.geom + a.gl.block_sums), a.num_rendered_dev + 1, a.prefiltered,
+        a.local_sort ? (uint32_t*)(a.img + a.il.tile_count) : nullptr);
     sr_count_launch();
     return cudaGetLastError();
 }

@@ -31,6 +31,7 @@ from . import _capi
 # --------------------------------------------------------------------------------------------
 _CAP_ALIGN = 256           # capacities are multiples of this so that bytes -> capacity is invertible
 _cap_hint: dict = {}       # (device index, W, H) -> last seen num_rendered
+_sort_global: set = set()  # keys for which a tile outgrew the shared-memory sort: use the global onesweep path
 _sync_mode = True          # True: read num_rendered back after every forward (like the reference)
 _pending: list = []        # nosync mode: (pinned host word, key, capacity) awaiting check_overflow()
 _host_pool: list = []      # pinned uint32[2] words, pre-allocated so that a forward never allocates pinned memory
@@ -106,6 +107,9 @@ def check_overflow(keep: bool = False):
     for host, key, cap in _pending:
         r, status = int(host[0]), int(host[1])
         _cap_hint[key] = max(_cap_hint.get(key, 0), r)
+        if status & _capi.SR_STATUS_SORT_CAP:
+            _sort_global.add(key)
+            bad = (r, cap)
         if status & _capi.SR_STATUS_OVERFLOW:
             bad = (r, cap)
     if not keep:
@@ -113,8 +117,8 @@ def check_overflow(keep: bool = False):
         _host_next = 0
     if bad:
         raise _capi.SurfelRasterError(
-            f"instance buffer overflow in nosync mode: num_rendered={bad[0]} > capacity={bad[1]}; "
-            "the frame was not rendered. Capacity hint updated -- re-run the step.")
+            f"instance buffer overflow (or a tile beyond the shared-memory sort) in nosync mode: num_rendered={bad[0]}, "
+            f"capacity={bad[1]}; the frame was not rendered. Hints updated -- re-run the step.")
 
 
 def _ptr(t):
@@ -173,12 +177,13 @@ class _CNamespace:
             geom = torch.empty((lib.sr_geom_bytes(P),), dtype=torch.uint8, device=dev)
             img = torch.empty((lib.sr_image_bytes(W, H),), dtype=torch.uint8, device=dev)
             nr_dev = torch.empty((2,), dtype=torch.int32, device=dev)
-            fr = _capi.SrFrame(P, int(degree), M, W, H, _as_float(tan_fovx), _as_float(tan_fovy),
-                               float(scale_modifier), int(bool(prefiltered)), int(bool(debug)))
             stream = torch.cuda.current_stream(dev)
             key = (dev.index, W, H)
             cap = _pick_capacity(key, P)
             while True:
+                fr = _capi.SrFrame(P, int(degree), M, W, H, _as_float(tan_fovx), _as_float(tan_fovy),
+                                   float(scale_modifier), int(bool(prefiltered)), int(bool(debug)),
+                                   0 if key in _sort_global else _capi.SR_FLAG_LOCAL_SORT)
                 binning = torch.empty((lib.sr_binning_bytes(cap, W, H),), dtype=torch.uint8, device=dev)
                 nosync = (not _sync_mode) and key in _cap_hint
                 host = _host_slot() if nosync else torch.empty((2,), dtype=torch.int32, pin_memory=True)
@@ -198,6 +203,9 @@ class _CNamespace:
                 _cap_hint[key] = max(_cap_hint.get(key, 0), num_rendered) if not _sync_mode else num_rendered
                 if status & _capi.SR_STATUS_PREFILTER:
                     raise RuntimeError("Point is filtered although prefiltered is set. This shouldn't happen!")
+                if status & _capi.SR_STATUS_SORT_CAP:
+                    _sort_global.add(key)          # some tile is too long for the shared-memory sort: global path
+                    continue
                 if status & _capi.SR_STATUS_OVERFLOW:
                     cap = _round_cap(int(num_rendered * 1.1) + 4096)
                     continue
@@ -228,7 +236,7 @@ class _CNamespace:
             if P > 0:
                 cap = _capacity_from_bytes(int(binningBuffer.numel()))
                 fr = _capi.SrFrame(P, int(degree), M, W, H, _as_float(tan_fovx), _as_float(tan_fovy),
-                                   float(scale_modifier), 0, int(bool(debug)))
+                                   float(scale_modifier), 0, int(bool(debug)), 0)
                 rc = lib.sr_backward(
                     C.byref(fr), _ptr(background), _ptr(means3D), _ptr(sh), _ptr(colors), _ptr(scales),
                     _ptr(rotations), _ptr(viewmatrix), _ptr(projmatrix), _ptr(campos), _ptr(radii),

@@ -59,6 +59,7 @@ def parse():
     ap.add_argument("--no-ref-cuda", action="store_true", help="skip timing the reference extension in the ours arm")
     ap.add_argument("--ref-device", default="cuda", choices=["cuda", "cpu"])
     ap.add_argument("--no-graph", action="store_true", help="keep the e2e step eager (no CUDA-graph capture)")
+    ap.add_argument("--no-fused", action="store_true", help="e2e through render() instead of render_fused()")
     return ap.parse_args()
 
 
@@ -259,7 +260,9 @@ def main():
         R_inst = int(frame_dev(0)[0][0])
 
     # ---------------- e2e arm: public API with host buffers ----------------
-    from vidu4d_b200.renderer import MiniCam, PipelineParams, render
+    from vidu4d_b200.renderer import MiniCam, PipelineParams, render as render_unfused, render_fused
+    # ours: the fused post-processing path of the public API; reference arm: the reference's own torch glue
+    render = render_fused if (args.impl == "ours" and not args.no_fused) else render_unfused
     pipe = PipelineParams()
     params = cloud.flat_params()
     fg = D.FlatGrads(params)
@@ -418,7 +421,7 @@ def main():
                        "parallelism": f"frames sharded over {world} GPU(s), 1 NCCL all-reduce of {acc_flat_bytes >> 20} MiB/step" if world > 1 else "1 GPU",
                        "l2": f"explicit flush (256 MiB write) between timed steps; per-step working set also exceeds the {L2_MB} MB L2"},
             "e2e": {"value": round(e2e_value, 2), "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
-                    "mode": e2e_mode,
+                    "mode": e2e_mode, "api": "render_fused" if render is render_fused else "render",
                     "what": "render() -> L1+normal+distortion loss -> backward -> (all-reduce) -> fused Adam; per step the "
                             "cameras + target images come from pinned host memory, the loss is read back"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels_ms": kernels,

@@ -148,6 +148,22 @@ typedef struct sr_debug_layout {
 } sr_debug_layout;
 SR_API int sr_debug_view(int32_t P, int32_t width, int32_t height, int64_t capacity, sr_debug_layout* out);
 
+/*
+ * Fused post-processing of `allmap`: everything gs/gaussian_renderer/__init__.py:121-162
+ * and gs/utils/point_utils.py:9-37 compute from the rasterizer's 8 planes, in one pass each way.
+ * world_view_transform is the camera's (4,4) W2C^T exactly as GaussianRasterizationSettings.viewmatrix.
+ * forward writes acc[HW], rend_normal[3HW], rend_dist[HW], depth_median[HW], depth_expected[HW], surf_depth[HW],
+ * surf_normal[3HW]; backward takes their gradients and writes g_allmap[8HW] (fully, no need to zero).
+ */
+SR_API int sr_post_forward(int32_t W, int32_t H, float tan_fovx, float tan_fovy, float depth_ratio, const float* allmap,
+                           const float* world_view_transform, float* acc, float* rend_normal, float* rend_dist,
+                           float* depth_median, float* depth_expected, float* surf_depth, float* surf_normal, void* stream);
+SR_API int sr_post_backward(int32_t W, int32_t H, float tan_fovx, float tan_fovy, float depth_ratio, const float* allmap,
+                            const float* world_view_transform, const float* surf_depth, const float* g_acc,
+                            const float* g_rend_normal, const float* g_rend_dist, const float* g_depth_median,
+                            const float* g_depth_expected, const float* g_surf_depth, const float* g_surf_normal,
+                            float* g_allmap, void* stream);
+
 SR_API int sr_abi_version(void);
 SR_API const char* sr_last_error(void);
 /* number of kernel launches issued by this library since load (bench.py's `gpu_launches`) */

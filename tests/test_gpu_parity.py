@@ -331,13 +331,13 @@ def test_local_and_global_sort_paths_agree_and_fallback(dev):
     inp = build_case(30000, 256, 192, 71, rigid=True)
     key = (dev.index, 256, 192)
     R._sort_global.discard(key)
-    a = _run_ours(inp, dev)
-    assert key not in R._sort_global
-    R._sort_global.add(key)
+    R._local_sort_default = True
     try:
-        b = _run_ours(inp, dev)
+        a = _run_ours(inp, dev)
+        assert key not in R._sort_global
     finally:
-        R._sort_global.discard(key)
+        R._local_sort_default = False
+    b = _run_ours(inp, dev)
     assert a["num_rendered"] == b["num_rendered"]
     for k in ("keys", "point_list", "ranges", "color", "allmap", "n_contrib"):
         assert torch.equal(a[k], b[k]), k
@@ -347,7 +347,11 @@ def test_local_and_global_sort_paths_agree_and_fallback(dev):
     inp = build_case(50000, 32, 32, 72)
     key = (dev.index, 32, 32)
     R._sort_global.discard(key)
-    r = _run_ours(inp, dev, with_grads=False)
+    R._local_sort_default = True
+    try:
+        r = _run_ours(inp, dev, with_grads=False)
+    finally:
+        R._local_sort_default = False
     assert key in R._sort_global, "the library should have switched this image size to the global sort"
     st = so.forward(inp["means3D"], inp["opacities"], inp["scales"], inp["rotations"], shs=inp["shs"], sh_degree=3, W=32, H=32,
                     tanfovx=0.5, tanfovy=0.5, bg=inp["bg"], viewmatrix=inp["viewmatrix"], projmatrix=inp["projmatrix"],
@@ -356,3 +360,36 @@ def test_local_and_global_sort_paths_agree_and_fallback(dev):
     np.testing.assert_array_equal(_np(r["point_list"]).astype(np.uint32), st.point_list)
     _assert_close_robust(_np(r["color"]), st.color, TOL, "color")
     R._sort_global.discard(key)
+
+
+def test_render_fused_matches_render(dev):
+    """render_fused() (one CUDA kernel each way for the allmap post-processing) == render() (the reference's torch
+    expressions, gaussian_renderer/__init__.py:121-162 + point_utils.py:9-37): values and parameter gradients."""
+    from vidu4d_b200.renderer import PipelineParams, make_camera, render, render_fused
+    from vidu4d_b200.synthetic import random_rotation
+    rng = np.random.default_rng(5)
+    Rc = random_rotation(rng)
+    # camera looking at the object from a rotated frame: camera-to-world rotation Rc, object kept at distance ~1
+    T = -Rc.T @ np.array([0.0, 0.0, 0.0]) + np.array([0.05, -0.03, 0.0])
+    cam = make_camera(160, 112, 2 * np.arctan(0.5), 2 * np.arctan(0.35), device=dev)
+    bg = torch.tensor([0.1, 0.3, 0.2], device=dev)
+    g = torch.Generator(device=dev).manual_seed(9)
+    wts = {k: torch.randn((c, 112, 160), device=dev, generator=g) for k, c in
+           (("render", 3), ("acc", 1), ("rend_normal", 3), ("rend_dist", 1), ("surf_depth", 3), ("render_depth_median", 3),
+            ("render_depth_expected", 3), ("surf_normal", 3))}
+    for depth_ratio in (0.0, 0.3):
+        grads = []
+        outs = []
+        for fn in (render, render_fused):
+            cloud = _cloud(6000, dev, seed=11)
+            out = fn(cam, cloud, PipelineParams(depth_ratio=depth_ratio), bg)
+            loss = sum((out[k] * w).sum() for k, w in wts.items())
+            loss.backward()
+            outs.append(out)
+            grads.append([p.grad.clone() for p in cloud.flat_params()])
+        for k in wts:
+            a, b = outs[0][k], outs[1][k]
+            assert a.shape == b.shape, k
+            assert float((a - b).abs().max()) <= 1e-5 * float(a.abs().max() + 1e-6), (k, depth_ratio)
+        for ga, gb in zip(*grads):
+            assert float((ga - gb).abs().max()) <= 1e-4 * float(ga.abs().max() + 1e-30), depth_ratio

@@ -20,7 +20,7 @@ SR_FLAG_LOCAL_SORT = 1
 SYMBOLS = (
     "sr_geom_bytes", "sr_image_bytes", "sr_binning_bytes", "sr_forward", "sr_backward",
     "sr_mark_visible", "sr_debug_view", "sr_abi_version", "sr_last_error", "sr_launch_count",
-    "sr_set_profiling", "sr_get_profile",
+    "sr_set_profiling", "sr_get_profile", "sr_post_forward", "sr_post_backward",
 )
 
 
@@ -81,6 +81,10 @@ def load():
     lib.sr_mark_visible.argtypes = [i32, f32p, f32p, f32p, vp, vp]
     lib.sr_debug_view.restype = C.c_int
     lib.sr_debug_view.argtypes = [i32, i32, i32, i64, C.POINTER(SrDebugLayout)]
+    lib.sr_post_forward.restype = C.c_int
+    lib.sr_post_forward.argtypes = [i32, i32, C.c_float, C.c_float, C.c_float] + [vp] * 10
+    lib.sr_post_backward.restype = C.c_int
+    lib.sr_post_backward.argtypes = [i32, i32, C.c_float, C.c_float, C.c_float] + [vp] * 12
     lib.sr_set_profiling.restype = None
     lib.sr_set_profiling.argtypes = [C.c_int]
     lib.sr_get_profile.restype = C.c_char_p

@@ -20,7 +20,7 @@
 
 namespace {
 
-constexpr uint32_t FLAG_AGG = 1u << 30, FLAG_INC = 2u << 30, FLAG_MASK = 3u << 30, VAL_MASK = ~FLAG_MASK;
+enum : uint32_t { FLAG_AGG = 1u << 30, FLAG_INC = 2u << 30, FLAG_MASK = 3u << 30, VAL_MASK = ~(3u << 30) };
 
 struct SortPlan {
     int npass;
@@ -157,14 +157,26 @@ onesweep_pass_kernel(uint64_t* __restrict__ keys0, uint64_t* __restrict__ keys1,
         atomicExch(&st[(size_t)tile * SR_SORT_BINS + tid], FLAG_INC | count);
     } else {
         atomicExch(&st[(size_t)tile * SR_SORT_BINS + tid], FLAG_AGG | count);
+        // windowed look-back: LB independent loads in flight per hop instead of one dependent load per
+        // predecessor (all tiles of a 0.5 M-key sort run in one wave, so nobody is "long finished")
+        constexpr int LB = 16;
         int t = (int)tile - 1;
         while (true) {
-            const uint32_t v = *((volatile uint32_t*)&st[(size_t)t * SR_SORT_BINS + tid]);
-            const uint32_t f = v & FLAG_MASK;
-            if (f == 0) continue;
-            excl += v & VAL_MASK;
-            if (f == FLAG_INC) break;
-            t--;
+            uint32_t v[LB];
+#pragma unroll
+            for (int q = 0; q < LB; q++)
+                v[q] = (t - q >= 0) ? *((volatile uint32_t*)&st[(size_t)(t - q) * SR_SORT_BINS + tid]) : FLAG_INC;
+            bool fin = false;
+            int q = 0;
+#pragma unroll
+            for (; q < LB; q++) {
+                const uint32_t f = v[q] & FLAG_MASK;
+                if (f == 0) break;                  // not published yet: re-read from here
+                excl += v[q] & VAL_MASK;
+                if (f == FLAG_INC) { fin = true; break; }
+            }
+            if (fin) break;
+            t -= q;
         }
         atomicExch(&st[(size_t)tile * SR_SORT_BINS + tid], FLAG_INC | (excl + count));
     }

@@ -55,7 +55,7 @@ tile_scan_kernel(const uint32_t* __restrict__ tile_count, int tiles, uint2* __re
         __syncthreads();
         const uint32_t excl = carry_s + wtot[warp] + inc - v;
         if (i < tiles) {
-            ranges[i] = make_uint2(excl, excl + v);
+            ranges[i] = v ? make_uint2(excl, excl + v) : make_uint2(0u, 0u);   // empty tiles stay (0,0) like the reference's memset
             atomicAdd(&cnt[v ? 32 - __clz(v) : 0], 1u);
             if (v > SR_LOCAL_SORT_CAP) atomicMax(&maxc_s, v);
         }
@@ -63,6 +63,7 @@ tile_scan_kernel(const uint32_t* __restrict__ tile_count, int tiles, uint2* __re
         if (threadIdx.x == 1023) carry_s = excl + v;
         __syncthreads();
     }
+    __shared__ uint32_t bad_s;
     if (threadIdx.x == 0) {
         const uint32_t R = carry_s;
         num_rendered[0] = R;
@@ -70,10 +71,15 @@ tile_scan_kernel(const uint32_t* __restrict__ tile_count, int tiles, uint2* __re
         if ((long long)R > capacity) st |= SR_STATUS_OVERFLOW;
         if (maxc_s) st |= SR_STATUS_SORT_CAP;
         if (st) atomicOr(num_rendered + 1, st);
+        bad_s = st;
         uint32_t acc = 0;
         for (int b = 32; b >= 0; b--) { start[b] = acc; acc += cnt[b]; }
     }
     __syncthreads();
+    if (bad_s) {
+        // frame abandoned: the composite kernels must see empty tiles (ranges may point past the capacity)
+        for (int t = threadIdx.x; t < tiles; t += 1024) ranges[t] = make_uint2(0u, 0u);
+    }
     // longest-list-first launch order for the per-tile kernels (same bucketing as sort.cu:tile_order_kernel)
     for (int t = threadIdx.x; t < tiles; t += 1024) {
         const uint32_t v = tile_count[t];

@@ -32,6 +32,7 @@ from . import _capi
 _CAP_ALIGN = 256           # capacities are multiples of this so that bytes -> capacity is invertible
 _cap_hint: dict = {}       # (device index, W, H) -> last seen num_rendered
 _sort_global: set = set()  # keys for which a tile outgrew the shared-memory sort: use the global onesweep path
+_local_sort_default = False  # the tile-local sort (SR_FLAG_LOCAL_SORT) is opt-in: see DESIGN.md section 3.2
 _sync_mode = True          # True: read num_rendered back after every forward (like the reference)
 _pending: list = []        # nosync mode: (pinned host word, key, capacity) awaiting check_overflow()
 _host_pool: list = []      # pinned uint32[2] words, pre-allocated so that a forward never allocates pinned memory
@@ -183,7 +184,7 @@ class _CNamespace:
             while True:
                 fr = _capi.SrFrame(P, int(degree), M, W, H, _as_float(tan_fovx), _as_float(tan_fovy),
                                    float(scale_modifier), int(bool(prefiltered)), int(bool(debug)),
-                                   0 if key in _sort_global else _capi.SR_FLAG_LOCAL_SORT)
+                                   _capi.SR_FLAG_LOCAL_SORT if (_local_sort_default and key not in _sort_global) else 0)
                 binning = torch.empty((lib.sr_binning_bytes(cap, W, H),), dtype=torch.uint8, device=dev)
                 nosync = (not _sync_mode) and key in _cap_hint
                 host = _host_slot() if nosync else torch.empty((2,), dtype=torch.int32, pin_memory=True)

@@ -233,6 +233,86 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=
     return rets
 
 
+class _RenderPost(torch.autograd.Function):
+    """allmap (8,H,W) -> (acc, rend_normal, rend_dist, depth_median, depth_expected, surf_depth, surf_normal) in one
+    CUDA kernel each way (csrc/postprocess.cu); same maths as the torch expressions in render()."""
+
+    @staticmethod
+    def forward(ctx, allmap, wvt, tanx, tany, depth_ratio):
+        from . import _capi
+        lib = _capi.load()
+        allmap = allmap.contiguous()
+        wvt = wvt.contiguous()
+        _, H, W = allmap.shape
+        dev = allmap.device
+        mk = lambda c: torch.empty((c, H, W), dtype=torch.float32, device=dev)  # noqa: E731
+        acc, rn, dist, med, ex, sd, sn = mk(1), mk(3), mk(1), mk(1), mk(1), mk(1), mk(3)
+        with torch.cuda.device(dev):
+            rc = lib.sr_post_forward(W, H, tanx, tany, depth_ratio, allmap.data_ptr(), wvt.data_ptr(), acc.data_ptr(),
+                                     rn.data_ptr(), dist.data_ptr(), med.data_ptr(), ex.data_ptr(), sd.data_ptr(),
+                                     sn.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+        _capi.check(rc, "sr_post_forward")
+        ctx.save_for_backward(allmap, wvt, sd)
+        ctx.cfg = (W, H, tanx, tany, depth_ratio)
+        return acc, rn, dist, med, ex, sd, sn
+
+    @staticmethod
+    def backward(ctx, g_acc, g_rn, g_dist, g_med, g_ex, g_sd, g_sn):
+        from . import _capi
+        lib = _capi.load()
+        allmap, wvt, sd = ctx.saved_tensors
+        W, H, tanx, tany, depth_ratio = ctx.cfg
+        dev = allmap.device
+        z = lambda g, c: torch.zeros((c, H, W), dtype=torch.float32, device=dev) if g is None else g.contiguous()  # noqa: E731
+        g_acc, g_rn, g_dist, g_med, g_ex, g_sd, g_sn = z(g_acc, 1), z(g_rn, 3), z(g_dist, 1), z(g_med, 1), z(g_ex, 1), z(g_sd, 1), z(g_sn, 3)
+        g_allmap = torch.empty_like(allmap)
+        with torch.cuda.device(dev):
+            rc = lib.sr_post_backward(W, H, tanx, tany, depth_ratio, allmap.data_ptr(), wvt.data_ptr(), sd.data_ptr(),
+                                      g_acc.data_ptr(), g_rn.data_ptr(), g_dist.data_ptr(), g_med.data_ptr(), g_ex.data_ptr(),
+                                      g_sd.data_ptr(), g_sn.data_ptr(), g_allmap.data_ptr(),
+                                      torch.cuda.current_stream(dev).cuda_stream)
+        _capi.check(rc, "sr_post_backward")
+        return g_allmap, None, None, None, None
+
+
+def render_fused(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=1.0, override_color=None):
+    """Same contract and dict keys as render(); the post-processing of `allmap` runs in one fused CUDA kernel each
+    way instead of ~35 forward / ~60 backward PyTorch kernels.  The three depth
+    entries are (3,H,W) broadcast VIEWS of one plane (render() materialises three copies with torch.cat)."""
+    xyz = pc.get_xyz
+    screenspace_points = torch.zeros_like(xyz, dtype=xyz.dtype, requires_grad=True, device=xyz.device) + 0
+    try:
+        screenspace_points.retain_grad()
+    except Exception:
+        pass
+    tanfovx = _tan_half(viewpoint_camera.FoVx)
+    tanfovy = _tan_half(viewpoint_camera.FoVy)
+    raster_settings = GaussianRasterizationSettings(
+        image_height=int(viewpoint_camera.image_height), image_width=int(viewpoint_camera.image_width),
+        tanfovx=tanfovx, tanfovy=tanfovy, bg=bg_color, scale_modifier=scaling_modifier,
+        viewmatrix=viewpoint_camera.world_view_transform, projmatrix=viewpoint_camera.full_proj_transform,
+        sh_degree=pc.active_sh_degree, campos=viewpoint_camera.camera_center, prefiltered=False, debug=False)
+    rasterizer = GaussianRasterizer(raster_settings=raster_settings)
+    scales = rotations = cov3D_precomp = None
+    if pipe.compute_cov3D_python:
+        cov3D_precomp = pc.get_covariance(scaling_modifier)
+    else:
+        scales, rotations = pc.get_scaling, pc.get_rotation
+    try:
+        xyz.retain_grad()
+    except Exception:
+        pass
+    rendered_image, radii, allmap = rasterizer(
+        means3D=xyz, means2D=screenspace_points, shs=pc.get_features, colors_precomp=override_color,
+        opacities=pc.get_opacity, scales=scales, rotations=rotations, cov3D_precomp=cov3D_precomp)
+    acc, rn, dist, med, ex, sd, sn = _RenderPost.apply(allmap, viewpoint_camera.world_view_transform, tanfovx, tanfovy,
+                                                       float(pipe.depth_ratio))
+    return {"render": rendered_image, "viewspace_points": screenspace_points, "visibility_filter": radii > 0,
+            "radii": radii, "acc": acc, "rend_normal": rn, "rend_dist": dist, "surf_depth": sd.expand(3, -1, -1),
+            "render_depth_median": med.expand(3, -1, -1), "render_depth_expected": ex.expand(3, -1, -1),
+            "surf_normal": sn}
+
+
 @dataclass
 class PipelineParams:
     """gs/arguments/__init__.py PipelineParams, as instantiated at deformable_gaussian.py:158-160."""

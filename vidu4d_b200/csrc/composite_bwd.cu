@@ -14,39 +14,39 @@
 namespace {
 using namespace comp;
 
-// recursive-halving sum of v[0..15] over the warp; afterwards lane L holds the total of component
-// comp(L) = 8*b4 + 4*b3 + 2*b2 + b1 (bits of L) in v[0] (both lanes of a pair hold the same total)
+// Recursive-halving sum of v[0..15] over each group of GL lanes (GL = 32, 16, 8 or 4).  Every step exchanges half
+// of the still-live values with the lane `off` away; afterwards a lane holds NV = max(1, 32/GL ... ) totals:
+//   GL=32 or 16: 1 value,  GL=8: 2 values,  GL=4: 4 values, of components  base(lane) + i,  i < NV  (see comp_base).
+template <int GL>
 __device__ __forceinline__ void butterfly16(float (&v)[16], int lane) {
-    {
-        const bool hi = lane & 16;
+    int n = 16;
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const float keep = hi ? v[i + 8] : v[i], send = hi ? v[i] : v[i + 8];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    for (int off = GL / 2; off >= 1; off >>= 1) {
+        if (n > 1) {
+            n >>= 1;
+            const bool hi = lane & off;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                if (i < n) {
+                    const float keep = hi ? v[i + n] : v[i], send = hi ? v[i] : v[i + n];
+                    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                }
+            }
+        } else {
+            v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
         }
     }
-    {
-        const bool hi = lane & 8;
+}
+// values a lane holds after butterfly16<GL>, and the component index of its first one
+template <int GL> struct BflyOut { static constexpr int NV = GL >= 16 ? 1 : 16 / GL; };
+template <int GL>
+__device__ __forceinline__ int comp_base(int lane) {
+    int c = 0, n = 16;
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const float keep = hi ? v[i + 4] : v[i], send = hi ? v[i] : v[i + 4];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-        }
+    for (int off = GL / 2; off >= 1; off >>= 1) {
+        if (n > 1) { n >>= 1; if (lane & off) c += n; }
     }
-    {
-        const bool hi = lane & 4;
-#pragma unroll
-        for (int i = 0; i < 2; i++) {
-            const float keep = hi ? v[i + 2] : v[i], send = hi ? v[i] : v[i + 2];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-        }
-    }
-    {
-        const bool hi = lane & 2;
-        const float keep = hi ? v[1] : v[0], send = hi ? v[0] : v[1];
-        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-    }
-    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+    return c;
 }
 
 // butterfly component index -> slot in the 20-float per-surfel accumulator (common.cuh SR_G_*):
@@ -55,6 +55,7 @@ __device__ __forceinline__ int comp_slot(int c) {
     return c < 9 ? SR_G_T + c : (c == 9 ? SR_G_OPAC : (c < 13 ? SR_G_COLOR + (c - 10) : SR_G_NORMAL + (c - 13)));
 }
 
+template <int G>
 __global__ void __launch_bounds__(32, 24)
 composite_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order, int tiles_x,
                      const float4* __restrict__ irec, int W, int H,
@@ -75,8 +76,11 @@ composite_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
     const int nb = (len + WB - 1) / WB;
     if (nb == 0) return;
 
+    using GS = GroupShape<G>;
     const int sx0 = (warp & 1) * 8, sy0 = (warp >> 1) * 4;
-    const int pix_x = tile_x * SR_TILE + sx0 + (lane & 7), pix_y = tile_y * SR_TILE + sy0 + (lane >> 3);
+    const int g = lane / GS::GL, l = lane % GS::GL;
+    const int pix_x = tile_x * SR_TILE + sx0 + GS::block_x(g) + l % GS::BW;
+    const int pix_y = tile_y * SR_TILE + sy0 + GS::block_y(g) + l / GS::BW;
     const bool inside = pix_x < W && pix_y < H;
     const float pixx = (float)pix_x + 0.5f, pixy = (float)pix_y + 0.5f;
     const size_t N = (size_t)W * H, pid = (size_t)W * pix_y + pix_x;
@@ -128,12 +132,13 @@ composite_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
         const float4* S = st[s];
         uint32_t cull = 0;
         if (lane < cnt) cull = __float_as_uint(S[lane * REC4 + 4].w);
-        const int cx0 = cull & 15, cx1 = (cull >> 4) & 15, cy0 = (cull >> 8) & 15, cy1 = (cull >> 12) & 15;
-        const bool hit = ((cull >> 16) & 1u) && cx0 <= sx0 + 7 && cx1 >= sx0 && cy0 <= sy0 + 3 && cy1 >= sy0;
-        uint32_t m = __ballot_sync(0xffffffffu, hit);
-        while (m) {
-            const int jj = 31 - __clz(m);
-            m &= ~(1u << jj);
+        // lane = instance: survivors of each group's pixel block (G ballots); every group then walks ITS list
+        // back to front, so up to G different instances are in flight per warp iteration
+        uint32_t mym = group_survivors<G>(cull, sx0, sy0, g);
+        while (__any_sync(0xffffffffu, mym != 0u)) {
+            const bool act = mym != 0u;
+            const int jj = act ? 31 - __clz(mym) : 0;
+            mym &= ~(1u << jj) | (act ? 0u : 0xffffffffu);
             const int pos = b * WB + jj;                       // == `contributor` after the decrement
             float v[16];
 #pragma unroll
@@ -141,7 +146,7 @@ composite_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
             float m2x = 0.f, m2y = 0.f;
             bool contrib = false, lowpass = false;
             const float rho_cut = cull_rho_cut(__shfl_sync(0xffffffffu, cull, jj));   // warp-uniform, before any divergence
-            if (pos < last_contributor) {
+            if (act && pos < last_contributor) {
                 const float4 r0 = S[jj * REC4], r1 = S[jj * REC4 + 1], r2 = S[jj * REC4 + 2];
                 // identical geometry / alpha arithmetic to the forward so that the skips agree
                 const float kx = ff(pixx, r1.z, -r0.x), ky = ff(pixx, r1.w, -r0.y), kz = ff(pixx, r2.x, -r0.z);
@@ -229,18 +234,26 @@ composite_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
                     }
                 }
             }
-            if (__any_sync(0xffffffffu, contrib)) {
+            const uint32_t cb = __ballot_sync(0xffffffffu, contrib);
+            if (cb) {
+                // this lane's group has a contributor?  (its REDs are skipped otherwise; the shuffles are warp-wide)
+                const bool gact = (cb >> (g * GS::GL)) & (GS::GL == 32 ? 0xffffffffu : ((1u << GS::GL) - 1u));
                 const uint32_t id = __float_as_uint(S[jj * REC4 + 4].z);
-                float* g = sgrad + (size_t)id * SR_GRAD_FLOATS;
-                butterfly16(v, lane);
-                if ((lane & 1) == 0) atomicAdd(g + comp_slot(lane >> 1), v[0]);
-                if (__any_sync(0xffffffffu, lowpass)) {
-                    // 2-value halving butterfly: lanes 0..15 end with sum(m2x), lanes 16..31 with sum(m2y)
-                    const bool hi = lane & 16;
-                    float w = (hi ? m2y : m2x) + __shfl_xor_sync(0xffffffffu, hi ? m2x : m2y, 16);
+                float* gp = sgrad + (size_t)id * SR_GRAD_FLOATS;
+                butterfly16<GS::GL>(v, lane);
+                constexpr int NV = BflyOut<GS::GL>::NV;
+                const int c0 = comp_base<GS::GL>(lane);
+                if (gact && (GS::GL < 32 || (lane & 1) == 0)) {
 #pragma unroll
-                    for (int o = 8; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
-                    if ((lane & 15) == 0) atomicAdd(g + SR_G_M2D + (lane >> 4), w);
+                    for (int i = 0; i < NV; i++) atomicAdd(gp + comp_slot(c0 + i), v[i]);
+                }
+                if (__any_sync(0xffffffffu, lowpass)) {
+                    // 2-value halving butterfly inside the group: its lane 0 ends with sum(m2x), lane GL/2 with sum(m2y)
+                    const bool hi = lane & (GS::GL / 2);
+                    float w = (hi ? m2y : m2x) + __shfl_xor_sync(0xffffffffu, hi ? m2x : m2y, GS::GL / 2);
+#pragma unroll
+                    for (int o = GS::GL / 4; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+                    if (gact && (l & (GS::GL / 2 - 1)) == 0) atomicAdd(gp + SR_G_M2D + (l >= GS::GL / 2 ? 1 : 0), w);
                 }
             }
         }
@@ -255,11 +268,19 @@ cudaError_t launch_composite_bwd(const BwdArgs& a) {
     cudaError_t e = cudaMemsetAsync(a.geom + a.gl.sgrad, 0, (size_t)(a.cam.P > 0 ? a.cam.P : 1) * SR_GRAD_FLOATS * 4, a.stream);
     if (e != cudaSuccess) return e;
     ProfileScope ps("composite_bwd", a.stream);
-    composite_bwd_kernel<<<a.il.tiles * 8, 32, 0, a.stream>>>(
-        (const uint2*)(a.img + a.il.ranges), (const uint32_t*)(a.img + a.il.tile_order), a.il.tiles_x,
-        (const float4*)(a.bin + a.bl.inst_rec), a.cam.W, a.cam.H, a.cam.bg,
-        (const float*)(a.img + a.il.final_T), (const uint32_t*)(a.img + a.il.n_contrib),
-        (const uint32_t*)(a.img + a.il.tile_last), a.dL_dcolor, a.dL_dothers, (float*)(a.geom + a.gl.sgrad));
+    auto launch = [&](auto kern) {
+        kern<<<a.il.tiles * 8, 32, 0, a.stream>>>(
+            (const uint2*)(a.img + a.il.ranges), (const uint32_t*)(a.img + a.il.tile_order), a.il.tiles_x,
+            (const float4*)(a.bin + a.bl.inst_rec), a.cam.W, a.cam.H, a.cam.bg,
+            (const float*)(a.img + a.il.final_T), (const uint32_t*)(a.img + a.il.n_contrib),
+            (const uint32_t*)(a.img + a.il.tile_last), a.dL_dcolor, a.dL_dothers, (float*)(a.geom + a.gl.sgrad));
+    };
+    switch (comp::groups_from_env()) {
+        case 1: launch(composite_bwd_kernel<1>); break;
+        case 2: launch(composite_bwd_kernel<2>); break;
+        case 8: launch(composite_bwd_kernel<8>); break;
+        default: launch(composite_bwd_kernel<4>); break;
+    }
     sr_count_launch();
     return cudaGetLastError();
 }

@@ -23,6 +23,7 @@ harness; if the .so is missing it falls back to the CPU oracle port and says so.
 from __future__ import annotations
 
 import argparse
+import contextlib
 import json
 import os
 import statistics
@@ -60,6 +61,7 @@ def parse():
     ap.add_argument("--ref-device", default="cuda", choices=["cuda", "cpu"])
     ap.add_argument("--no-graph", action="store_true", help="keep the e2e step eager (no CUDA-graph capture)")
     ap.add_argument("--no-fused", action="store_true", help="e2e through render() instead of render_fused()")
+    ap.add_argument("--streams", type=int, default=2, help="CUDA streams the frames of a step alternate over (value arm)")
     return ap.parse_args()
 
 
@@ -155,6 +157,10 @@ def main():
     D.init_distributed("nccl", device)
     F, K, Wm, RES, P = args.frames_per_step, args.steps, max(args.warmup, 3), args.res, args.surfels
 
+    try:
+        torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)   # frames deliberately run on 2 streams
+    except Exception:
+        pass
     from vidu4d_b200 import _capi, rasterizer as RZ, renderer as RN
     if args.impl == "reference":
         from oracle import ref_ext
@@ -208,13 +214,34 @@ def main():
 
     flat_acc = torch.zeros((acc_flat_bytes // 4,), device=device)
 
+    # Frames of a step are independent: alternate them over `--streams` CUDA streams so that one frame's tail
+    # (a few long composite warps, r1e ncu: SMs ~20 % idle) overlaps the next frame's head.  Gradients accumulate
+    # per stream and are summed once per step.
+    NS = max(1, args.streams) if args.impl == "ours" else 1
+    side = [torch.cuda.Stream(device=device) for _ in range(max(NS, 2))]
+    accs = [acc] + [[torch.zeros_like(a) for a in acc] for _ in range(NS - 1)]
+
     def step_dev(step):
         R_last = 0
+        main = torch.cuda.current_stream()
+        if NS > 1:
+            for st_ in side:
+                st_.wait_stream(main)
         for f in range(F):
-            o, gr = frame_dev(view_of(step, f))
-            # gr = (dmeans2D, dcolors, dopacity, dmeans3D, dtransMat, dsh, dscales, drots)
-            acc[0].add_(gr[3]); acc[1].add_(gr[5]); acc[2].add_(gr[2]); acc[3].add_(gr[6]); acc[4].add_(gr[7])
-            R_last = o[0]
+            k = f % NS
+            ctx = torch.cuda.stream(side[k]) if NS > 1 else contextlib.nullcontext()
+            with ctx:
+                o, gr = frame_dev(view_of(step, f))
+                # gr = (dmeans2D, dcolors, dopacity, dmeans3D, dtransMat, dsh, dscales, drots)
+                a_ = accs[k]
+                a_[0].add_(gr[3]); a_[1].add_(gr[5]); a_[2].add_(gr[2]); a_[3].add_(gr[6]); a_[4].add_(gr[7])
+                R_last = o[0]
+        if NS > 1:
+            for st_ in side:
+                main.wait_stream(st_)
+            for k in range(1, NS):
+                for a0, ak in zip(accs[0], accs[k]):
+                    a0.add_(ak); ak.zero_()
         if world > 1:
             torch.cat([a.reshape(-1) for a in acc], out=flat_acc)
             torch.distributed.all_reduce(flat_acc)
@@ -282,18 +309,35 @@ def main():
             v = view_of(step, f)
             cam_h[f, 0] = torch.from_numpy(vms_h[v]); cam_h[f, 1] = torch.from_numpy(pms_h[v]); cps_hh[f] = torch.from_numpy(cps_h[v])
 
+    e2e_streams = [1]
+    tots = [torch.zeros((), device=device) for _ in range(4)]
+
     def body():
-        """H2D of this step's inputs -> render x F -> loss -> backward (everything a CUDA graph can hold)."""
+        """H2D of this step's inputs -> render x F -> loss -> backward (everything a CUDA graph can hold).  Frames
+        alternate over e2e_streams[0] streams; autograd runs each frame's backward on its forward stream and
+        serialises the accumulation into the (flat) .grad buffers itself."""
+        ns = e2e_streams[0]
+        main = torch.cuda.current_stream()
         tg.copy_(targets_h, non_blocking=True); cam.copy_(cam_h, non_blocking=True); cp.copy_(cps_hh, non_blocking=True)
         fg.zero_()
-        tot.zero_()
+        for t_ in tots:
+            t_.zero_()
+        if ns > 1:
+            for k in range(ns):
+                side[k].wait_stream(main)
         for f in range(F):
-            view = MiniCam(RES, RES, fov, fov, 0.01, 100.0, cam[f, 0], cam[f, 1], cp[f])
-            out = render(view, cloud, pipe, bg)
-            loss = (out["render"] - tg[f]).abs().mean() + 0.05 * (1.0 - (out["rend_normal"] * out["surf_normal"]).sum(0)).mean() \
-                + 0.01 * out["rend_dist"].mean()
-            loss.backward()
-            tot.add_(loss.detach())
+            k = f % ns
+            with (torch.cuda.stream(side[k]) if ns > 1 else contextlib.nullcontext()):
+                view = MiniCam(RES, RES, fov, fov, 0.01, 100.0, cam[f, 0], cam[f, 1], cp[f])
+                out = render(view, cloud, pipe, bg)
+                loss = (out["render"] - tg[f]).abs().mean() + 0.05 * (1.0 - (out["rend_normal"] * out["surf_normal"]).sum(0)).mean() \
+                    + 0.01 * out["rend_dist"].mean()
+                loss.backward()
+                tots[k].add_(loss.detach())
+        if ns > 1:
+            for k in range(ns):
+                main.wait_stream(side[k])
+        tot.copy_(tots[0] + tots[1] + tots[2] + tots[3])
 
     def tail():
         fg.allreduce_(average_over=F * world)
@@ -317,25 +361,45 @@ def main():
     if args.impl == "ours" and not args.no_graph:
         # The sync-free forward makes the whole step capturable: one cudaGraphLaunch replaces ~150 small launches.
         # (The reference cannot be captured: its forward blocks on a D2H copy, rasterizer_impl.cu:282.)
-        try:
-            for s_ in range(2):
-                step_e2e(s_)                                   # eager warm-up: allocator pools, caches, capacity hints
-            RZ.check_overflow()
-            RZ.reserve_host_slots(F + 4)
-            gph = torch.cuda.CUDAGraph()
-            side = torch.cuda.Stream(device=device)
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                fill_host(0); body(); RZ.check_overflow()       # once on the side stream, as torch recommends
-            torch.cuda.current_stream().wait_stream(side)
-            RZ.reserve_host_slots(F + 4)
-            with torch.cuda.graph(gph):
-                body()
-            graph, e2e_mode = gph, "cuda_graph(H2D+render+loss+backward) + eager all-reduce/Adam/readback"
-        except Exception as ex:   # pragma: no cover
-            sys.stderr.write(f"[bench] CUDA-graph capture of the e2e step failed, staying eager: {ex!r}\n")
-            graph = None
-            RZ._pending.clear()
+        for ns_try in ([min(NS, 2), 1] if NS > 1 else [1]):
+            try:
+                e2e_streams[0] = ns_try
+                for s_ in range(2):
+                    step_e2e(s_)                               # eager warm-up: allocator pools, caches, capacity hints
+                RZ.check_overflow()
+                RZ.reserve_host_slots(F + 4)
+                gph = torch.cuda.CUDAGraph()
+                warm = torch.cuda.Stream(device=device)
+                warm.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(warm):
+                    fill_host(0); body(); RZ.check_overflow()   # once on a side stream, as torch recommends
+                torch.cuda.current_stream().wait_stream(warm)
+                torch.cuda.synchronize()
+                RZ.reserve_host_slots(F + 4)
+                with torch.cuda.graph(gph):
+                    body()
+                graph = gph
+                e2e_mode = f"cuda_graph(H2D+render+loss+backward, {ns_try} stream(s)) + eager all-reduce/Adam/readback"
+                break
+            except Exception as ex:   # pragma: no cover
+                sys.stderr.write(f"[bench] CUDA-graph capture of the e2e step ({ns_try} streams) failed: {ex!r}\n")
+                graph = None
+                e2e_streams[0] = 1
+                RZ._pending.clear()
+                torch.cuda.synchronize()
+
+    # sanity of the captured multi-stream step against a plain eager single-stream step on the same inputs
+    e2e_check = None
+    if graph is not None:
+        l_graph = step_e2e(1000)
+        g_graph = fg.flat.clone()
+        keep_graph, keep_ns = graph, e2e_streams[0]
+        graph, e2e_streams[0] = None, 1
+        l_eager = step_e2e(1000)
+        g_eager = fg.flat.clone()
+        graph, e2e_streams[0] = keep_graph, keep_ns
+        e2e_check = {"loss_graph": l_graph, "loss_eager": l_eager,
+                     "grad_rel_diff": float((g_graph - g_eager).abs().max() / (g_eager.abs().max() + 1e-30))}
 
     e2e_total, _, _ = timed(step_e2e, K, Wm)
     e2e_total = max_over_ranks(e2e_total, world, device)
@@ -419,9 +483,10 @@ def main():
                                    f"{F} frames/step/GPU on orbiting cameras, colour+depth+normal+distortion fwd+bwd",
                        "surfels": P, "resolution": RES, "frames_per_step_per_gpu": F, "instances_per_frame": R_inst,
                        "parallelism": f"frames sharded over {world} GPU(s), 1 NCCL all-reduce of {acc_flat_bytes >> 20} MiB/step" if world > 1 else "1 GPU",
+                       "streams": NS,
                        "l2": f"explicit flush (256 MiB write) between timed steps; per-step working set also exceeds the {L2_MB} MB L2"},
             "e2e": {"value": round(e2e_value, 2), "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
-                    "mode": e2e_mode, "api": "render_fused" if render is render_fused else "render",
+                    "mode": e2e_mode, "check_vs_eager": e2e_check, "api": "render_fused" if render is render_fused else "render",
                     "what": "render() -> L1+normal+distortion loss -> backward -> (all-reduce) -> fused Adam; per step the "
                             "cameras + target images come from pinned host memory, the loss is read back"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels_ms": kernels,

@@ -278,8 +278,8 @@ cudaError_t launch_composite_bwd(const BwdArgs& a) {
     switch (comp::groups_from_env()) {
         case 1: launch(composite_bwd_kernel<1>); break;
         case 2: launch(composite_bwd_kernel<2>); break;
-        case 8: launch(composite_bwd_kernel<8>); break;
-        default: launch(composite_bwd_kernel<4>); break;
+        case 4: launch(composite_bwd_kernel<4>); break;
+        default: launch(composite_bwd_kernel<8>); break;
     }
     sr_count_launch();
     return cudaGetLastError();

@@ -174,8 +174,8 @@ cudaError_t launch_composite_fwd(const FwdArgs& a) {
     switch (G) {
         case 1: launch(composite_fwd_kernel<1>); break;
         case 2: launch(composite_fwd_kernel<2>); break;
-        case 8: launch(composite_fwd_kernel<8>); break;
-        default: launch(composite_fwd_kernel<4>); break;
+        case 4: launch(composite_fwd_kernel<4>); break;
+        default: launch(composite_fwd_kernel<8>); break;
     }
     sr_count_launch();
     return cudaGetLastError();

@@ -56,19 +56,25 @@ __device__ __forceinline__ int comp_slot(int c) {
 }
 
 template <int G>
-__global__ void __launch_bounds__(32, 24)
-composite_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order, int tiles_x,
+__global__ void __launch_bounds__(32 * WPC, 24 / WPC)
+composite_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order, int n_items, int tiles_x,
                      const float4* __restrict__ irec, int W, int H,
                      const float* __restrict__ bg, const float* __restrict__ final_Ts,
                      const uint32_t* __restrict__ n_contrib, const uint32_t* __restrict__ sub_last,
                      const float* __restrict__ dL_dpixels, const float* __restrict__ dL_dothers,
                      float* __restrict__ sgrad) {
-    // one warp per CTA: work item = (tile, 8x4 sub-tile), tiles in longest-list-first order
-    __shared__ __align__(128) float4 st[NST][WB * REC4];
-    __shared__ __align__(8) uint64_t bar[NST];
+    // WPC independent warps per CTA (the SM holds at most 32 CTAs): work item = (tile, 8x4 sub-tile), tiles in
+    // longest-list-first order; the warps of a CTA share nothing
+    __shared__ __align__(128) float4 st_all[WPC][NST][WB * REC4];
+    __shared__ __align__(8) uint64_t bar_all[WPC][NST];
+    float4 (*st)[WB * REC4] = st_all[threadIdx.x >> 5];
+    uint64_t* bar = bar_all[threadIdx.x >> 5];
 
-    const int lane = threadIdx.x, warp = blockIdx.x & 7;
-    const int tile = (int)tile_order[blockIdx.x >> 3];
+    const int lane = threadIdx.x & 31;
+    const int item = blockIdx.x * WPC + (threadIdx.x >> 5);
+    if (item >= n_items) return;
+    const int warp = item & 7;
+    const int tile = (int)tile_order[item >> 3];
     const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
     const uint2 range = ranges[tile];
     // nothing beyond this sub-tile's deepest contributor matters
@@ -125,6 +131,11 @@ composite_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
     float last_alpha = 0.f, last_depth = 0.f, accum_depth_rec = 0.f, accum_alpha_rec = 0.f, last_dL_dT = 0.f;
     float accum_n0 = 0.f, accum_n1 = 0.f, accum_n2 = 0.f, last_n0 = 0.f, last_n1 = 0.f, last_n2 = 0.f;
 
+    // deepest list position any pixel of this lane's GROUP needs: later positions are dropped from its survivor mask
+    int group_last = last_contributor;
+#pragma unroll
+    for (int o = GS::GL / 2; o > 0; o >>= 1) group_last = max(group_last, __shfl_xor_sync(0xffffffffu, group_last, o));
+
     for (int k = 0; k < nb; k++) {
         const int b = nb - 1 - k, s = k % NST;
         mbar_wait(&bar[s], (uint32_t)((k / NST) & 1));
@@ -135,6 +146,10 @@ composite_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
         // lane = instance: survivors of each group's pixel block (G ballots); every group then walks ITS list
         // back to front, so up to G different instances are in flight per warp iteration
         uint32_t mym = group_survivors<G>(cull, sx0, sy0, g);
+        {
+            const int keep = group_last - b * WB;             // positions b*WB + jj with jj >= keep contribute nothing
+            mym &= keep >= 32 ? 0xffffffffu : (keep <= 0 ? 0u : ((1u << keep) - 1u));
+        }
         while (__any_sync(0xffffffffu, mym != 0u)) {
             const bool act = mym != 0u;
             const int jj = act ? 31 - __clz(mym) : 0;
@@ -269,8 +284,8 @@ cudaError_t launch_composite_bwd(const BwdArgs& a) {
     if (e != cudaSuccess) return e;
     ProfileScope ps("composite_bwd", a.stream);
     auto launch = [&](auto kern) {
-        kern<<<a.il.tiles * 8, 32, 0, a.stream>>>(
-            (const uint2*)(a.img + a.il.ranges), (const uint32_t*)(a.img + a.il.tile_order), a.il.tiles_x,
+        kern<<<(a.il.tiles * 8 + comp::WPC - 1) / comp::WPC, 32 * comp::WPC, 0, a.stream>>>(
+            (const uint2*)(a.img + a.il.ranges), (const uint32_t*)(a.img + a.il.tile_order), a.il.tiles * 8, a.il.tiles_x,
             (const float4*)(a.bin + a.bl.inst_rec), a.cam.W, a.cam.H, a.cam.bg,
             (const float*)(a.img + a.il.final_T), (const uint32_t*)(a.img + a.il.n_contrib),
             (const uint32_t*)(a.img + a.il.tile_last), a.dL_dcolor, a.dL_dothers, (float*)(a.geom + a.gl.sgrad));

@@ -20,17 +20,24 @@ namespace {
 using namespace comp;
 
 template <int G>
-__global__ void __launch_bounds__(32)
-composite_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order, int tiles_x,
+__global__ void __launch_bounds__(32 * WPC)
+composite_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order, int n_items, int tiles_x,
                      const float4* __restrict__ irec, int W, int H,
                      const float* __restrict__ bg, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
                      float* __restrict__ out_color, float* __restrict__ out_others, uint32_t* __restrict__ sub_last) {
     using GS = GroupShape<G>;
-    __shared__ __align__(128) float4 st[NST][WB * REC4];
-    __shared__ __align__(8) uint64_t bar[NST];
+    // WPC independent warps per CTA (the SM holds at most 32 CTAs): work item = (tile, 8x4 sub-tile), tiles in
+    // longest-list-first order; the warps of a CTA share nothing
+    __shared__ __align__(128) float4 st_all[WPC][NST][WB * REC4];
+    __shared__ __align__(8) uint64_t bar_all[WPC][NST];
+    float4 (*st)[WB * REC4] = st_all[threadIdx.x >> 5];
+    uint64_t* bar = bar_all[threadIdx.x >> 5];
 
-    const int lane = threadIdx.x, warp = blockIdx.x & 7;
-    const int tile = (int)tile_order[blockIdx.x >> 3];
+    const int lane = threadIdx.x & 31;
+    const int item = blockIdx.x * WPC + (threadIdx.x >> 5);
+    if (item >= n_items) return;
+    const int warp = item & 7;
+    const int tile = (int)tile_order[item >> 3];
     const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
     const uint2 range = ranges[tile];
     const int len = (int)(range.y - range.x);
@@ -73,6 +80,11 @@ composite_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
         if (lane < cnt) cull = __float_as_uint(S[lane * REC4 + 4].w);
         // lane = instance: which groups' blocks does this instance's cull rectangle touch?  (G ballots)
         uint32_t mym = group_survivors<G>(cull, sx0, sy0, g);
+        {   // a group whose pixels are all finished must not keep the warp iterating over its survivors
+            const uint32_t db = __ballot_sync(0xffffffffu, done);
+            const uint32_t gm = (GS::GL == 32 ? 0xffffffffu : ((1u << GS::GL) - 1u)) << (g * GS::GL);
+            if ((db & gm) == gm) mym = 0u;
+        }
         while (__any_sync(0xffffffffu, mym != 0u)) {
             const bool act = mym != 0u;
             const int jj = act ? __ffs(mym) - 1 : 0;
@@ -165,8 +177,8 @@ cudaError_t launch_composite_fwd(const FwdArgs& a) {
     ProfileScope ps("composite_fwd", a.stream);
     const int G = comp::groups_from_env();
     auto launch = [&](auto kern) {
-        kern<<<a.il.tiles * 8, 32, 0, a.stream>>>(
-            (const uint2*)(a.img + a.il.ranges), (const uint32_t*)(a.img + a.il.tile_order), a.il.tiles_x,
+        kern<<<(a.il.tiles * 8 + comp::WPC - 1) / comp::WPC, 32 * comp::WPC, 0, a.stream>>>(
+            (const uint2*)(a.img + a.il.ranges), (const uint32_t*)(a.img + a.il.tile_order), a.il.tiles * 8, a.il.tiles_x,
             (const float4*)(a.bin + a.bl.inst_rec), a.cam.W, a.cam.H, a.cam.bg,
             (float*)(a.img + a.il.final_T), (uint32_t*)(a.img + a.il.n_contrib), a.out_color, a.out_others,
             (uint32_t*)(a.img + a.il.tile_last));

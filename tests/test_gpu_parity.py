@@ -396,3 +396,17 @@ def test_render_fused_matches_render(dev):
             assert float((a.detach() - b.detach()).abs().max()) <= tol * float(a.detach().abs().max() + 1e-6), (k, depth_ratio)
         for ga, gb in zip(*grads):
             assert float((ga - gb).abs().max()) <= 1e-3 * float(ga.abs().max() + 1e-30), depth_ratio
+
+
+def test_stage3_standin_loss_decreases(dev):
+    """configs[2] in miniature: bob-skinning warp (PyTorch) -> render_fused -> loss -> Adam, non-leaf rasterizer inputs,
+    in-place learnable-background edit of the render before backward.  The loss must go down."""
+    import importlib.util
+    import os
+    from .conftest import ROOT
+    spec = importlib.util.spec_from_file_location("stage3_standin", os.path.join(ROOT, "examples", "stage3_standin.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    r = m.run(surfels=20000, res=128, frames=8, steps=60, bones=12, log_every=10, quiet=True)
+    first, last = r["losses"][0][1], r["losses"][-1][1]
+    assert np.isfinite(last) and last < 0.8 * first, r["losses"]

@@ -410,3 +410,37 @@ def test_stage3_standin_loss_decreases(dev):
     r = m.run(surfels=20000, res=128, frames=8, steps=60, bones=12, log_every=10, quiet=True)
     first, last = r["losses"][0][1], r["losses"][-1][1]
     assert np.isfinite(last) and last < 0.8 * first, r["losses"]
+
+
+@pytest.mark.parametrize("M,deg", [(1, 0), (4, 1), (9, 2), (16, 1)])
+def test_sh_coefficient_counts_against_oracle(M, deg, dev):
+    """shs with fewer than 16 coefficients per surfel (M = sh.size(1)) and an active degree below the stored one:
+    exercises the generic (non-float4) staging paths of preprocess_fwd / surfel_bwd."""
+    from oracle import surfel_oracle as so
+    from tests.golden.make_golden import build_case
+    inp = build_case(3000, 96, 80, 80 + M, sh_degree=deg)
+    inp["shs"] = np.ascontiguousarray(inp["shs"][:, :M])
+    r = _run_ours(inp, dev)
+    st = so.forward(inp["means3D"], inp["opacities"], inp["scales"], inp["rotations"], shs=inp["shs"], sh_degree=deg, W=96, H=80,
+                    tanfovx=0.5, tanfovy=0.5, bg=inp["bg"], viewmatrix=inp["viewmatrix"], projmatrix=inp["projmatrix"],
+                    campos=inp["campos"])
+    og = so.backward(st, inp["dL_dcolor"], inp["dL_dallmap"])
+    np.testing.assert_array_equal(_np(r["point_list"]).astype(np.uint32), st.point_list)
+    _assert_close_robust(_np(r["color"]), st.color, TOL, "color")
+    assert r["grads"]["dL_dsh"].shape == (3000, M, 3)
+    for k in GRADS:
+        _assert_close_robust(_np(r["grads"][k]), og[k], TOL, k)
+    used = (deg + 1) ** 2
+    assert float(r["grads"]["dL_dsh"][:, used:].abs().sum()) == 0.0     # coefficients above the active degree get no gradient
+
+
+def test_prefiltered_flag_reports_culled_surfels(dev):
+    """The reference __trap()s when `prefiltered` is set and a surfel is culled (auxiliary.h:175-183); we raise."""
+    from tests.golden.make_golden import build_case
+    from vidu4d_b200 import rasterizer as R
+    inp = build_case(600, 64, 64, 16, center=(0.0, 0.0, 0.45), sh_degree=0)       # part of the cloud is behind z = 0.2
+    t = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in inp.items() if k != "meta"}
+    e = torch.empty((0,), device=dev)
+    with pytest.raises(RuntimeError, match="prefiltered"):
+        R._C.rasterize_gaussians(t["bg"], t["means3D"], e, t["opacities"], t["scales"], t["rotations"], 1.0, e, t["viewmatrix"],
+                                 t["projmatrix"], 0.5, 0.5, 64, 64, t["shs"], 0, t["campos"], True, False)

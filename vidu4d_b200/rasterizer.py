@@ -56,7 +56,7 @@ def _pick_capacity(key, P: int) -> int:
     r = _cap_hint.get(key)
     if r is None:
         return _round_cap(max(4 * P, 4096))
-    return _round_cap(int(r * 1.25) + 4096)
+    return _round_cap(int(r * 1.5) + 4096)     # headroom for frame-to-frame growth in nosync mode (104 B / instance)
 
 
 _bytes_to_cap: dict = {}

@@ -33,12 +33,14 @@
 #define SR_R_W19 19
 
 // ---- gradient accumulator layout (float index), one per surfel ----------------------------
-//  0..8 dL/dT   9,10 dL/dmean2D (low-pass branch)   11 dL/dopacity   12..14 dL/dcolor   15..17 dL/dnormal
+//  0..8 dL/dT   9 dL/dopacity   10..12 dL/dcolor   13..15 dL/dnormal   16,17 dL/dmean2D (low-pass branch)
+//  Slots 0..15 are, in order, the 16 components of the composite backward's butterfly, so that a lane's 2 or 4
+//  consecutive totals leave as ONE 8- or 16-byte vector reduction (REDG.ADD.F32x2 / x4).
 #define SR_G_T 0
-#define SR_G_M2D 9
-#define SR_G_OPAC 11
-#define SR_G_COLOR 12
-#define SR_G_NORMAL 15
+#define SR_G_OPAC 9
+#define SR_G_COLOR 10
+#define SR_G_NORMAL 13
+#define SR_G_M2D 16
 
 #define SR_LOCAL_SORT_CAP 8192   // max instances of one tile the tile-local sort holds in shared memory
 #define SR_STATUS_SORT_CAP 8u     // status bit: a tile exceeded it -- re-run with the global onesweep path

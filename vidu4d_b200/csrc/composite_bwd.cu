@@ -49,10 +49,18 @@ __device__ __forceinline__ int comp_base(int lane) {
     return c;
 }
 
-// butterfly component index -> slot in the 20-float per-surfel accumulator (common.cuh SR_G_*):
-// v[] order: 0..8 dT, 9 dopacity, 10..12 dcolor, 13..15 dnormal
-__device__ __forceinline__ int comp_slot(int c) {
-    return c < 9 ? SR_G_T + c : (c == 9 ? SR_G_OPAC : (c < 13 ? SR_G_COLOR + (c - 10) : SR_G_NORMAL + (c - 13)));
+// v[] order: 0..8 dT, 9 dopacity, 10..12 dcolor, 13..15 dnormal == slots 0..15 of the per-surfel accumulator
+static_assert(SR_G_T == 0 && SR_G_OPAC == 9 && SR_G_COLOR == 10 && SR_G_NORMAL == 13, "butterfly order == accumulator order");
+// NV consecutive totals -> one vector reduction (red.global.add.v2/v4.f32, sm_90+; address 4*NV-byte aligned)
+template <int NV>
+__device__ __forceinline__ void red_add(float* p, const float (&v)[16]) {
+    if constexpr (NV == 4) {
+        asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" :: "l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+    } else if constexpr (NV == 2) {
+        asm volatile("red.global.v2.f32.add [%0], {%1, %2};" :: "l"(p), "f"(v[0]), "f"(v[1]) : "memory");
+    } else {
+        atomicAdd(p, v[0]);
+    }
 }
 
 template <int G>
@@ -258,10 +266,7 @@ composite_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
                 butterfly16<GS::GL>(v, lane);
                 constexpr int NV = BflyOut<GS::GL>::NV;
                 const int c0 = comp_base<GS::GL>(lane);
-                if (gact && (GS::GL < 32 || (lane & 1) == 0)) {
-#pragma unroll
-                    for (int i = 0; i < NV; i++) atomicAdd(gp + comp_slot(c0 + i), v[i]);
-                }
+                if (gact && (GS::GL < 32 || (lane & 1) == 0)) red_add<NV>(gp + c0, v);
                 if (__any_sync(0xffffffffu, lowpass)) {
                     // 2-value halving butterfly inside the group: its lane 0 ends with sum(m2x), lane GL/2 with sum(m2y)
                     const bool hi = lane & (GS::GL / 2);

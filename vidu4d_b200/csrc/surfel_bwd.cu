@@ -118,9 +118,11 @@ surfel_bwd_body(const CamParams& c, const int idx, const int M, float* osh, cons
     const float4* g4 = sgrad + (size_t)idx * 5;
     const float4 g0 = g4[0], g1 = g4[1], g2 = g4[2], g3 = g4[3], g4v = g4[4];
     float dT[9] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w, g2.x};
-    const float dmx = g2.y, dmy = g2.z, dop = g2.w;
-    const float dcol[3] = {g3.x, g3.y, g3.z};
-    const float dnr[3] = {g3.w, g4v.x, g4v.y};
+    // accumulator layout: common.cuh SR_G_*
+    const float dop = g2.y;
+    const float dcol[3] = {g2.z, g2.w, g3.x};
+    const float dnr[3] = {g3.y, g3.z, g3.w};
+    const float dmx = g4v.x, dmy = g4v.y;
     const float4* r4 = srec + (size_t)idx * 5;
     const float4 r0 = __ldg(r4), r1 = __ldg(r4 + 1), r2 = __ldg(r4 + 2);
     const float T[9] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x};

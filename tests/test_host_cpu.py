@@ -33,12 +33,14 @@ def test_buffer_sizing_monotonic_and_invertible(built):
     prev = 0
     for cap in (256, 512, 4096, 100_096, 1_000_192, 3_000_064):
         assert cap == _round_cap(cap)
-        b = lib.sr_binning_bytes(cap, 0, 0)
+        b = lib.sr_binning_bytes(cap, 512, 512)
         assert b > prev
-        assert _capacity_from_bytes(b) == cap
+        assert _capacity_from_bytes(b, 512, 512) == cap
+        # the per-stage contribution masks make the size depend on the tile count too
+        assert lib.sr_binning_bytes(cap, 1024, 1024) > b
         prev = b
     with pytest.raises(_capi.SurfelRasterError):
-        _capacity_from_bytes(prev + 1)
+        _capacity_from_bytes(prev + 1, 512, 512)
 
 
 def test_debug_layout_is_aligned(built):

@@ -119,13 +119,15 @@ const char* sr_get_profile(void) {
 
 size_t sr_geom_bytes(int32_t P) { return geom_layout(P).total; }
 size_t sr_image_bytes(int32_t width, int32_t height) { return image_layout(width, height).total; }
-size_t sr_binning_bytes(int64_t capacity, int32_t, int32_t) { return bin_layout(capacity).total; }
+size_t sr_binning_bytes(int64_t capacity, int32_t width, int32_t height) {
+    return bin_layout(capacity, image_layout(width > 0 ? width : 0, height > 0 ? height : 0).tiles).total;
+}
 
 int sr_debug_view(int32_t P, int32_t width, int32_t height, int64_t capacity, sr_debug_layout* out) {
     if (!out) return fail(SR_EINVAL, "out is NULL");
     const GeomLayout g = geom_layout(P);
     const ImageLayout i = image_layout(width, height);
-    const BinLayout b = bin_layout(capacity);
+    const BinLayout b = bin_layout(capacity, i.tiles);
     out->surfel_rec = g.surfel_rec; out->depths = g.depths; out->tiles_touched = g.tiles_touched;
     out->point_offsets = g.point_offsets; out->clamped = g.clamped;
     out->keys[0] = b.keys[0]; out->keys[1] = b.keys[1]; out->values[0] = b.values[0]; out->values[1] = b.values[1];
@@ -170,7 +172,7 @@ int sr_forward(const sr_frame* f, const float* background, const float* means3D,
     a.scales = scales; a.rotations = rotations;
     a.out_color = out_color; a.out_others = out_others; a.radii = radii;
     a.geom = (char*)geom_buffer; a.bin = (char*)binning_buffer; a.img = (char*)image_buffer;
-    a.gl = geom_layout(P); a.bl = bin_layout(capacity); a.il = image_layout(f->width, f->height);
+    a.gl = geom_layout(P); a.il = image_layout(f->width, f->height); a.bl = bin_layout(capacity, a.il.tiles);
     a.num_rendered_dev = num_rendered_dev;
     a.prefiltered = f->prefiltered;
     a.key_bits = 32 + (int)sr_higher_msb((uint32_t)a.il.tiles);
@@ -226,7 +228,7 @@ int sr_backward(const sr_frame* f, const float* background, const float* means3D
     a.means3D = means3D; a.shs = shs; a.colors_precomp = colors_precomp; a.scales = scales; a.rotations = rotations;
     a.radii = radii; a.dL_dcolor = dL_dout_color; a.dL_dothers = dL_dout_others;
     a.geom = (char*)geom_buffer; a.bin = (char*)binning_buffer; a.img = (char*)image_buffer;
-    a.gl = geom_layout(f->P); a.bl = bin_layout(capacity); a.il = image_layout(f->width, f->height);
+    a.gl = geom_layout(f->P); a.il = image_layout(f->width, f->height); a.bl = bin_layout(capacity, a.il.tiles);
     a.dL_dmeans2D = dL_dmeans2D; a.dL_dcolors = dL_dcolors; a.dL_dopacity = dL_dopacity; a.dL_dmeans3D = dL_dmeans3D;
     a.dL_dtransMat = dL_dtransMat; a.dL_dsh = dL_dsh; a.dL_dscales = dL_dscales; a.dL_drotations = dL_drotations;
     a.stream = stream; a.debug = debug;

@@ -42,6 +42,7 @@
 #define SR_G_NORMAL 13
 #define SR_G_M2D 16
 
+#define SR_CONTRIB_STAGE_WORDS 64   // 8 sub-tiles x 8 groups, one 32-bit instance mask each
 #define SR_LOCAL_SORT_CAP 8192   // max instances of one tile the tile-local sort holds in shared memory
 #define SR_STATUS_SORT_CAP 8u     // status bit: a tile exceeded it -- re-run with the global onesweep path
 #define SR_SORT_MAX_PASSES 8
@@ -70,7 +71,7 @@ struct ImageLayout {
     int tiles_x, tiles_y, tiles;
 };
 struct BinLayout {
-    size_t keys[2], values[2], inst_rec, sort_ctl, hist, status, total;
+    size_t keys[2], values[2], inst_rec, contrib, sort_ctl, hist, status, total;
     int64_t capacity;
     int sort_tiles;
 };
@@ -104,7 +105,7 @@ static inline __host__ __device__ ImageLayout image_layout(int W, int H) {
     L.total = o;
     return L;
 }
-static inline __host__ __device__ BinLayout bin_layout(int64_t capacity) {
+static inline __host__ __device__ BinLayout bin_layout(int64_t capacity, int tiles) {
     BinLayout L;
     size_t C = capacity > 0 ? (size_t)capacity : 1, o = 0;
     L.capacity = (int64_t)C;
@@ -114,6 +115,10 @@ static inline __host__ __device__ BinLayout bin_layout(int64_t capacity) {
     L.values[0] = o; o = sr_align_up(o + C * 4);
     L.values[1] = o; o = sr_align_up(o + C * 4);
     L.inst_rec = o;  o = sr_align_up(o + C * SR_REC_FLOATS * 4);
+    // contribution masks: per (32-instance stage of a tile list, 8x4 sub-tile, lane group) the instances that
+    // contributed to at least one pixel of the group's block -- written by the forward composite, walked by the
+    // backward.  Stage s of tile t lives at index (range.x >> 5) + t + s  (<= capacity/32 + tiles in total).
+    L.contrib = o;   o = sr_align_up(o + ((C >> 5) + (size_t)(tiles > 0 ? tiles : 0) + 1) * SR_CONTRIB_STAGE_WORDS * 4);
     // the three below are zeroed together by one memset at the start of every forward
     L.sort_ctl = o;  o = sr_align_up(o + SR_CTL_WORDS * 4);
     L.hist = o;      o = sr_align_up(o + (size_t)SR_SORT_MAX_PASSES * SR_SORT_BINS * 4);

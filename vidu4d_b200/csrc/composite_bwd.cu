@@ -70,7 +70,7 @@ composite_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
                      const float* __restrict__ bg, const float* __restrict__ final_Ts,
                      const uint32_t* __restrict__ n_contrib, const uint32_t* __restrict__ sub_last,
                      const float* __restrict__ dL_dpixels, const float* __restrict__ dL_dothers,
-                     float* __restrict__ sgrad) {
+                     const uint32_t* __restrict__ contrib_masks, float* __restrict__ sgrad) {
     // WPC independent warps per CTA (the SM holds at most 32 CTAs): work item = (tile, 8x4 sub-tile), tiles in
     // longest-list-first order; the warps of a CTA share nothing
     __shared__ __align__(128) float4 st_all[WPC][NST][WB * REC4];
@@ -142,25 +142,26 @@ composite_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
     float accum_depth_rec = 0.f, accum_alpha_rec = 0.f, last_dL_dT = 0.f;
     float accum_n0 = 0.f, accum_n1 = 0.f, accum_n2 = 0.f;
 
-    // deepest list position any pixel of this lane's GROUP needs: later positions are dropped from its survivor mask
-    int group_last = last_contributor;
-#pragma unroll
-    for (int o = GS::GL / 2; o > 0; o >>= 1) group_last = max(group_last, __shfl_xor_sync(0xffffffffu, group_last, o));
+    // the forward recorded, per stage, which instances contributed to at least one pixel of this group's block
+    // (common.cuh bin_layout: contrib): exactly the survivors worth evaluating -- no cull test, no trimming
+    const uint32_t* cm_in = contrib_masks + (((size_t)(range.x >> 5) + tile) * 8 + warp) * 8 + g;
+    uint32_t next_mask = __ldg(cm_in + (size_t)(nb - 1) * SR_CONTRIB_STAGE_WORDS);
 
     for (int k = 0; k < nb; k++) {
         const int b = nb - 1 - k, s = k % NST;
+        uint32_t mym = next_mask;
+        if (b > 0) next_mask = __ldg(cm_in + (size_t)(b - 1) * SR_CONTRIB_STAGE_WORDS);   // lands during this stage
+        if (!__any_sync(0xffffffffu, mym != 0u)) {
+            // nothing of this stage reached any pixel of the sub-tile: recycle its slot without touching it
+            mbar_wait(&bar[s], (uint32_t)((k / NST) & 1));
+            if (lane == 0 && k + NST < nb) issue(k + NST);
+            continue;
+        }
         mbar_wait(&bar[s], (uint32_t)((k / NST) & 1));
         const int cnt = min(WB, len - b * WB);
         const float4* S = st[s];
         uint32_t cull = 0;
         if (lane < cnt) cull = __float_as_uint(S[lane * REC4 + 4].w);
-        // lane = instance: survivors of each group's pixel block (G ballots); every group then walks ITS list
-        // back to front, so up to G different instances are in flight per warp iteration
-        uint32_t mym = group_survivors<G>(cull, sx0, sy0, g);
-        {
-            const int keep = group_last - b * WB;             // positions b*WB + jj with jj >= keep contribute nothing
-            mym &= keep >= 32 ? 0xffffffffu : (keep <= 0 ? 0u : ((1u << keep) - 1u));
-        }
         while (__any_sync(0xffffffffu, mym != 0u)) {
             const bool act = mym != 0u;
             const int jj = act ? 31 - __clz(mym) : 0;
@@ -294,7 +295,8 @@ cudaError_t launch_composite_bwd(const BwdArgs& a) {
             (const uint2*)(a.img + a.il.ranges), (const uint32_t*)(a.img + a.il.tile_order), a.il.tiles * 8, a.il.tiles_x,
             (const float4*)(a.bin + a.bl.inst_rec), a.cam.W, a.cam.H, a.cam.bg,
             (const float*)(a.img + a.il.final_T), (const uint32_t*)(a.img + a.il.n_contrib),
-            (const uint32_t*)(a.img + a.il.tile_last), a.dL_dcolor, a.dL_dothers, (float*)(a.geom + a.gl.sgrad));
+            (const uint32_t*)(a.img + a.il.tile_last), a.dL_dcolor, a.dL_dothers,
+            (const uint32_t*)(a.bin + a.bl.contrib), (float*)(a.geom + a.gl.sgrad));
     };
     switch (comp::groups_from_env()) {
         case 1: launch(composite_bwd_kernel<1>); break;

@@ -24,7 +24,8 @@ __global__ void __launch_bounds__(32 * WPC)
 composite_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order, int n_items, int tiles_x,
                      const float4* __restrict__ irec, int W, int H,
                      const float* __restrict__ bg, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
-                     float* __restrict__ out_color, float* __restrict__ out_others, uint32_t* __restrict__ sub_last) {
+                     float* __restrict__ out_color, float* __restrict__ out_others, uint32_t* __restrict__ sub_last,
+                     uint32_t* __restrict__ contrib_masks) {
     using GS = GroupShape<G>;
     // WPC independent warps per CTA (the SM holds at most 32 CTAs): work item = (tile, 8x4 sub-tile), tiles in
     // longest-list-first order; the warps of a CTA share nothing
@@ -70,6 +71,10 @@ composite_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
     float dist1 = 0.f, dist2 = 0.f, distortion = 0.f, median_depth = 0.f, median_weight = 0.f;
     uint32_t median_contributor = 0, last_contributor = 0;
     bool done = !inside;
+    // instances of the current stage that contributed to this lane's pixel; OR-ed over the group at the end of the
+    // stage and kept for the backward (common.cuh bin_layout: contrib)
+    uint32_t cmask = 0u;
+    uint32_t* cm_out = contrib_masks + (((size_t)(range.x >> 5) + tile) * 8 + warp) * 8 + g;
 
     for (int b = 0; b < nb; b++) {
         const int s = b % NST;
@@ -134,8 +139,13 @@ composite_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
             C2 = ff(T, fm(alpha, r4.y), C2);
             T = test_T;
             last_contributor = contributor;
+            cmask |= 1u << jj;
         }
         __syncwarp();                                   // every lane is done reading stage s
+#pragma unroll
+        for (int o = GS::GL / 2; o > 0; o >>= 1) cmask |= __shfl_xor_sync(0xffffffffu, cmask, o);
+        if (l == 0) cm_out[(size_t)b * SR_CONTRIB_STAGE_WORDS] = cmask;
+        cmask = 0u;
         if (__all_sync(0xffffffffu, done)) {
             // drain the copies still in flight before this warp (and its CTA's smem) goes away
             for (int b2 = b + 1; b2 < nb && b2 < b + NST; b2++) mbar_wait(&bar[b2 % NST], (uint32_t)((b2 / NST) & 1));
@@ -181,7 +191,7 @@ cudaError_t launch_composite_fwd(const FwdArgs& a) {
             (const uint2*)(a.img + a.il.ranges), (const uint32_t*)(a.img + a.il.tile_order), a.il.tiles * 8, a.il.tiles_x,
             (const float4*)(a.bin + a.bl.inst_rec), a.cam.W, a.cam.H, a.cam.bg,
             (float*)(a.img + a.il.final_T), (uint32_t*)(a.img + a.il.n_contrib), a.out_color, a.out_others,
-            (uint32_t*)(a.img + a.il.tile_last));
+            (uint32_t*)(a.img + a.il.tile_last), (uint32_t*)(a.bin + a.bl.contrib));
     };
     switch (G) {
         case 1: launch(composite_fwd_kernel<1>); break;

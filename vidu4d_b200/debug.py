@@ -12,7 +12,7 @@ from .rasterizer import _capacity_from_bytes
 
 def decode(geomBuffer, binningBuffer, imgBuffer, P: int, W: int, H: int, num_rendered: int) -> dict:
     lib = _capi.load()
-    cap = _capacity_from_bytes(int(binningBuffer.numel()))
+    cap = _capacity_from_bytes(int(binningBuffer.numel()), W, H)
     L = _capi.SrDebugLayout()
     _capi.check(lib.sr_debug_view(P, W, H, cap, C.byref(L)), "sr_debug_view")
     N, R = W * H, int(num_rendered)

@@ -62,22 +62,23 @@ def _pick_capacity(key, P: int) -> int:
 _bytes_to_cap: dict = {}
 
 
-def _capacity_from_bytes(nbytes: int) -> int:
-    """Inverse of sr_binning_bytes for capacities that are multiples of _CAP_ALIGN."""
-    if nbytes in _bytes_to_cap:
-        return _bytes_to_cap[nbytes]
+def _capacity_from_bytes(nbytes: int, W: int, H: int) -> int:
+    """Inverse of sr_binning_bytes(., W, H) for capacities that are multiples of _CAP_ALIGN."""
+    key = (nbytes, W, H)
+    if key in _bytes_to_cap:
+        return _bytes_to_cap[key]
     lib = _capi.load()
     lo, hi = 1, 1 << 22   # in units of _CAP_ALIGN
     while lo < hi:
         mid = (lo + hi) // 2
-        if lib.sr_binning_bytes(mid * _CAP_ALIGN, 0, 0) < nbytes:
+        if lib.sr_binning_bytes(mid * _CAP_ALIGN, W, H) < nbytes:
             lo = mid + 1
         else:
             hi = mid
     cap = lo * _CAP_ALIGN
-    if lib.sr_binning_bytes(cap, 0, 0) != nbytes:
+    if lib.sr_binning_bytes(cap, W, H) != nbytes:
         raise _capi.SurfelRasterError("binningBuffer was not produced by this library's forward")
-    _bytes_to_cap[nbytes] = cap
+    _bytes_to_cap[key] = cap
     return cap
 
 
@@ -235,7 +236,7 @@ class _CNamespace:
             dL_dopacity, dL_dtransMat, dL_dsh = mk(P, 1), mk(P, 9), mk(P, M, 3)
             dL_dscales, dL_drotations = mk(P, 2), mk(P, 4)
             if P > 0:
-                cap = _capacity_from_bytes(int(binningBuffer.numel()))
+                cap = _capacity_from_bytes(int(binningBuffer.numel()), W, H)
                 fr = _capi.SrFrame(P, int(degree), M, W, H, _as_float(tan_fovx), _as_float(tan_fovy),
                                    float(scale_modifier), 0, int(bool(debug)), 0)
                 rc = lib.sr_backward(

@@ -62,7 +62,7 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="keep the e2e step eager (no CUDA-graph capture)")
     ap.add_argument("--no-fused", action="store_true", help="e2e through render() instead of render_fused()")
     ap.add_argument("--e2e-streams", type=int, default=1, help="(debug) streams of the eager e2e step when --no-graph")
-    ap.add_argument("--streams", type=int, default=2, help="CUDA streams the frames of a step alternate over (value arm)")
+    ap.add_argument("--streams", type=int, default=4, help="CUDA streams the frames of a step alternate over (value arm)")
     return ap.parse_args()
 
 
@@ -159,7 +159,7 @@ def main():
     F, K, Wm, RES, P = args.frames_per_step, args.steps, max(args.warmup, 3), args.res, args.surfels
 
     try:
-        torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)   # frames deliberately run on 2 streams
+        torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)   # frames deliberately run on several streams
     except Exception:
         pass
     from vidu4d_b200 import _capi, rasterizer as RZ, renderer as RN
@@ -319,7 +319,9 @@ def main():
         serialises the accumulation into the (flat) .grad buffers itself."""
         ns = e2e_streams[0]
         main = torch.cuda.current_stream()
-        tg.copy_(targets_h, non_blocking=True); cam.copy_(cam_h, non_blocking=True); cp.copy_(cps_hh, non_blocking=True)
+        # cameras up front (small); each frame's target image is uploaded on the stream that renders the frame, so the
+        # copy engine works while the other streams' frames compute (same bytes per step, nothing cached across steps)
+        cam.copy_(cam_h, non_blocking=True); cp.copy_(cps_hh, non_blocking=True)
         fg.zero_()
         for t_ in tots:
             t_.zero_()
@@ -329,6 +331,7 @@ def main():
         for f in range(F):
             k = f % ns
             with (torch.cuda.stream(side[k]) if ns > 1 else contextlib.nullcontext()):
+                tg[f].copy_(targets_h[f], non_blocking=True)
                 view = MiniCam(RES, RES, fov, fov, 0.01, 100.0, cam[f, 0], cam[f, 1], cp[f])
                 out = render(view, cloud, pipe, bg)
                 loss = (out["render"] - tg[f]).abs().mean() + 0.05 * (1.0 - (out["rend_normal"] * out["surf_normal"]).sum(0)).mean() \
@@ -365,7 +368,7 @@ def main():
     if args.impl == "ours" and not args.no_graph:
         # The sync-free forward makes the whole step capturable: one cudaGraphLaunch replaces ~150 small launches.
         # (The reference cannot be captured: its forward blocks on a D2H copy, rasterizer_impl.cu:282.)
-        for ns_try in ([min(NS, 2), 1] if NS > 1 else [1]):
+        for ns_try in (sorted({min(NS, 4), min(NS, 2), 1}, reverse=True) if NS > 1 else [1]):
             try:
                 e2e_streams[0] = ns_try
                 for s_ in range(2):
@@ -434,6 +437,10 @@ def main():
     peak_src = "MEASURED_PEAKS.json (measured)" if peaks else "B200_PROFILING.md fallback 6650 GB/s"
     N = RES * RES
     if args.impl == "ours" and rank == 0:
+        # single stream, nothing else in flight: the per-kernel CUDA events must not span another stream's work
+        for f in range(2):
+            frame_dev(f % NVIEWS)
+        torch.cuda.synchronize()
         _capi.get_profile()
         _capi.set_profiling(True)
         nprof = 6

@@ -4,11 +4,13 @@
 //
 // The reference issues up to 16 global float atomics per contributing (pixel, surfel) pair
 // (backward.cu:345-446).  Here (DESIGN.md "composite backward"):
-//   * same tiling, warp-autonomous TMA-fed instance stream and sub-tile culling as the forward, walked back to
-//     front, starting at the sub-tile's deepest contributor recorded by the forward (no work on the occluded tail);
-//   * the 16 per-pair gradient components are reduced across the 32 pixels of a warp with a recursive-halving
-//     butterfly (16 shuffles) and leave the SM as ONE 16-lane global reduction per (sub-tile, instance) --
-//     64 contiguous bytes of the surfel's accumulator -- instead of 16 scalar atomics per contributing pixel.
+//   * same tiling and warp-autonomous TMA-fed instance stream as the forward, walked back to front, starting at the
+//     sub-tile's deepest contributor recorded by the forward (no work on the occluded tail);
+//   * the survivors of a stage are NOT re-derived: the forward left, per stage and 2x2 group, the mask of instances
+//     that contributed to a pixel of the group -- exactly the pairs worth evaluating;
+//   * the 16 per-pair gradient components are reduced across the pixels of a group with a recursive-halving
+//     butterfly and leave the SM as ONE 16-byte vector reduction per lane (REDG.ADD.F32x4) into the surfel's
+//     accumulator, whose first 16 floats are in butterfly order -- instead of 16 scalar atomics per contributing pixel.
 #include "composite_common.cuh"
 
 namespace {

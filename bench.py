@@ -213,14 +213,23 @@ def main():
                                                       vms[v], pms[v], TAN, TAN, dLc, dLo, t_in["shs"], 3, cps[v], o[4],
                                                       o[0], o[5], o[6], False)
 
-    flat_acc = torch.zeros((acc_flat_bytes // 4,), device=device)
-
     # Frames of a step are independent: alternate them over `--streams` CUDA streams so that one frame's tail
-    # (a few long composite warps, r1e ncu: SMs ~20 % idle) overlaps the next frame's head.  Gradients accumulate
-    # per stream and are summed once per step.
+    # (a few long composite warps, ncu: SMs 14-20 % idle) overlaps other frames' heads.  Each stream sums the
+    # gradients of its frames into its own row of one [streams, floats] buffer (first frame of the step assigns, the
+    # rest add); one reduction over the rows per step gives the step's flat gradient -- the buffer the all-reduce uses.
     NS = max(1, args.streams) if args.impl == "ours" else 1
     side = [torch.cuda.Stream(device=device) for _ in range(max(NS, 2))]
-    accs = [acc] + [[torch.zeros_like(a) for a in acc] for _ in range(NS - 1)]
+    nflt = acc_flat_bytes // 4
+    stack = torch.zeros((NS, nflt), device=device)
+    flat_acc = torch.zeros((nflt,), device=device) if NS > 1 else stack[0]
+
+    def views(row):
+        out, o_ = [], 0
+        for a in acc:
+            out.append(row[o_:o_ + a.numel()].view(a.shape)); o_ += a.numel()
+        return out
+    accs = [views(stack[k]) for k in range(NS)]
+    GIDX = (3, 5, 2, 6, 7)      # gr = (dmeans2D, dcolors, dopacity, dmeans3D, dtransMat, dsh, dscales, drots)
 
     def step_dev(step):
         R_last = 0
@@ -233,18 +242,20 @@ def main():
             ctx = torch.cuda.stream(side[k]) if NS > 1 else contextlib.nullcontext()
             with ctx:
                 o, gr = frame_dev(view_of(step, f))
-                # gr = (dmeans2D, dcolors, dopacity, dmeans3D, dtransMat, dsh, dscales, drots)
-                a_ = accs[k]
-                a_[0].add_(gr[3]); a_[1].add_(gr[5]); a_[2].add_(gr[2]); a_[3].add_(gr[6]); a_[4].add_(gr[7])
+                for a_, gi in zip(accs[k], GIDX):
+                    if f < NS:
+                        a_.copy_(gr[gi].view(a_.shape))
+                    else:
+                        a_.add_(gr[gi].view(a_.shape))
                 R_last = o[0]
         if NS > 1:
             for st_ in side:
                 main.wait_stream(st_)
-            for k in range(1, NS):
-                for a0, ak in zip(accs[0], accs[k]):
-                    a0.add_(ak); ak.zero_()
+            if F >= NS:
+                torch.sum(stack, dim=0, out=flat_acc)
+            else:
+                torch.sum(stack[:F], dim=0, out=flat_acc)
         if world > 1:
-            torch.cat([a.reshape(-1) for a in acc], out=flat_acc)
             torch.distributed.all_reduce(flat_acc)
         if args.impl == "ours":
             RZ.check_overflow()     # the step's only host<->device synchronisation

@@ -62,7 +62,7 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="keep the e2e step eager (no CUDA-graph capture)")
     ap.add_argument("--no-fused", action="store_true", help="e2e through render() instead of render_fused()")
     ap.add_argument("--e2e-streams", type=int, default=1, help="(debug) streams of the eager e2e step when --no-graph")
-    ap.add_argument("--streams", type=int, default=4, help="CUDA streams the frames of a step alternate over (value arm)")
+    ap.add_argument("--streams", type=int, default=8, help="CUDA streams the frames of a step alternate over (value arm)")
     return ap.parse_args()
 
 
@@ -218,7 +218,7 @@ def main():
     # gradients of its frames into its own row of one [streams, floats] buffer (first frame of the step assigns, the
     # rest add); one reduction over the rows per step gives the step's flat gradient -- the buffer the all-reduce uses.
     NS = max(1, args.streams) if args.impl == "ours" else 1
-    side = [torch.cuda.Stream(device=device) for _ in range(max(NS, 2))]
+    side = [torch.cuda.Stream(device=device) for _ in range(max(NS, 2))]   # also used by the e2e step
     nflt = acc_flat_bytes // 4
     stack = torch.zeros((NS, nflt), device=device)
     flat_acc = torch.zeros((nflt,), device=device) if NS > 1 else stack[0]
@@ -322,7 +322,7 @@ def main():
             cam_h[f, 0] = torch.from_numpy(vms_h[v]); cam_h[f, 1] = torch.from_numpy(pms_h[v]); cps_hh[f] = torch.from_numpy(cps_h[v])
 
     e2e_streams = [1]
-    tots = [torch.zeros((), device=device) for _ in range(4)]
+    tots = [torch.zeros((), device=device) for _ in range(8)]
 
     def body():
         """H2D of this step's inputs -> render x F -> loss -> backward (everything a CUDA graph can hold).  Frames
@@ -352,7 +352,7 @@ def main():
         if ns > 1:
             for k in range(ns):
                 main.wait_stream(side[k])
-        tot.copy_(tots[0] + tots[1] + tots[2] + tots[3])
+        tot.copy_(torch.stack(tots).sum())
 
     freeze = [False]
 
@@ -379,7 +379,7 @@ def main():
     if args.impl == "ours" and not args.no_graph:
         # The sync-free forward makes the whole step capturable: one cudaGraphLaunch replaces ~150 small launches.
         # (The reference cannot be captured: its forward blocks on a D2H copy, rasterizer_impl.cu:282.)
-        for ns_try in (sorted({min(NS, 4), min(NS, 2), 1}, reverse=True) if NS > 1 else [1]):
+        for ns_try in (sorted({min(NS, 8, F), min(NS, 4), min(NS, 2), 1}, reverse=True) if NS > 1 else [1]):
             try:
                 e2e_streams[0] = ns_try
                 for s_ in range(2):

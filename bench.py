@@ -294,6 +294,13 @@ def main():
         o_probe = RZ._C.rasterize_gaussians(bg, t_in["means3D"], e, t_in["opac"], t_in["scales"], t_in["rots"], 1.0, e, vms[0],
                                             pms[0], TAN, TAN, RES, RES, t_in["shs"], 3, cps[0], False, False)
         R_inst = int(o_probe[0])
+        # secondary, explanatory figure: (pixel, instance) pair evaluations of the probe frame, as the
+        # upper bound 256 x tile-list length summed over tiles (what a tile-wide walk would evaluate)
+        from vidu4d_b200 import debug as _dbg
+        _dec = _dbg.decode(o_probe[4], o_probe[5], o_probe[6], P, RES, RES, R_inst)
+        _rg = _dec["ranges"].to(torch.int64)
+        pair_upper = int(((_rg[:, 1] - _rg[:, 0]) * 256).sum().item())
+        del _dec, _rg
         RZ.set_sync_mode(False)
     else:
         R_inst = int(frame_dev(0)[0][0])
@@ -484,6 +491,8 @@ def main():
                     "frac": round(ach / hbm_peak, 5), "traffic": traffic, "peak_source": peak_src,
                     "note": "the composite kernels are FP32-issue/shared-memory bound by construction (SURVEY 8d); "
                             "algorithmic HBM bytes are small, see profiles/ for ncu pipe utilisation",
+                    "pair_evals_upper_per_frame": pair_upper,
+                    "pair_evals_upper_per_s": round(pair_upper * (K * F * world) / (total_ms * 1e-3), 0),
                     "frame_alg_MB": round((1002 * P + 324 * R_inst + 128 * N) / 1e6, 1),
                     "frame_GBps": round((1002 * P + 324 * R_inst + 128 * N) / 1e9 / (total_ms * 1e-3 / (K * F)), 1)}
 

@@ -42,7 +42,7 @@
 #define SR_G_NORMAL 13
 #define SR_G_M2D 16
 
-#define SR_CONTRIB_STAGE_WORDS 64   // 8 sub-tiles x 8 groups, one 32-bit instance mask each
+#define SR_CONTRIB_STAGE_WORDS 256  // 8 sub-tiles x 32 pixels, one 32-bit instance mask each (1 KB per stage)
 #define SR_LOCAL_SORT_CAP 8192   // max instances of one tile the tile-local sort holds in shared memory
 #define SR_STATUS_SORT_CAP 8u     // status bit: a tile exceeded it -- re-run with the global onesweep path
 #define SR_SORT_MAX_PASSES 8
@@ -115,9 +115,9 @@ static inline __host__ __device__ BinLayout bin_layout(int64_t capacity, int til
     L.values[0] = o; o = sr_align_up(o + C * 4);
     L.values[1] = o; o = sr_align_up(o + C * 4);
     L.inst_rec = o;  o = sr_align_up(o + C * SR_REC_FLOATS * 4);
-    // contribution masks: per (32-instance stage of a tile list, 8x4 sub-tile, lane group) the instances that
-    // contributed to at least one pixel of the group's block -- written by the forward composite, walked by the
-    // backward.  Stage s of tile t lives at index (range.x >> 5) + t + s  (<= capacity/32 + tiles in total).
+    // contribution masks: per (32-instance stage of a tile list, 8x4 sub-tile, pixel) the instances that
+    // contributed to the pixel -- written by the forward composite, walked by the backward.
+    // Stage s of tile t lives at index (range.x >> 5) + t + s  (<= capacity/32 + tiles in total).
     L.contrib = o;   o = sr_align_up(o + ((C >> 5) + (size_t)(tiles > 0 ? tiles : 0) + 1) * SR_CONTRIB_STAGE_WORDS * 4);
     // the three below are zeroed together by one memset at the start of every forward
     L.sort_ctl = o;  o = sr_align_up(o + SR_CTL_WORDS * 4);

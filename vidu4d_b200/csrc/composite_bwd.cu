@@ -56,7 +56,11 @@ static_assert(SR_G_T == 0 && SR_G_OPAC == 9 && SR_G_COLOR == 10 && SR_G_NORMAL =
 // NV consecutive totals -> one vector reduction (red.global.add.v2/v4.f32, sm_90+; address 4*NV-byte aligned)
 template <int NV>
 __device__ __forceinline__ void red_add(float* p, const float (&v)[16]) {
-    if constexpr (NV == 4) {
+    if constexpr (NV == 16 || NV == 8) {
+#pragma unroll
+        for (int q = 0; q < NV; q += 4)
+            asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" :: "l"(p + q), "f"(v[q]), "f"(v[q + 1]), "f"(v[q + 2]), "f"(v[q + 3]) : "memory");
+    } else if constexpr (NV == 4) {
         asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" :: "l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
     } else if constexpr (NV == 2) {
         asm volatile("red.global.v2.f32.add [%0], {%1, %2};" :: "l"(p), "f"(v[0]), "f"(v[1]) : "memory");
@@ -144,40 +148,37 @@ composite_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
     float accum_depth_rec = 0.f, accum_alpha_rec = 0.f, last_dL_dT = 0.f;
     float accum_n0 = 0.f, accum_n1 = 0.f, accum_n2 = 0.f;
 
-    // the forward recorded, per stage, which instances contributed to at least one pixel of this group's block
-    // (common.cuh bin_layout: contrib): exactly the survivors worth evaluating -- no cull test, no trimming
-    const uint32_t* cm_in = contrib_masks + (((size_t)(range.x >> 5) + tile) * 8 + warp) * 8 + g;
+    // The forward recorded, per stage and pixel, which instances contributed (common.cuh bin_layout: contrib).  A group
+    // walks the union of its pixels' masks -- exactly the instances worth visiting: no cull test, no trimming, and a
+    // lane knows beforehand whether ITS pixel takes part, so the alpha / depth tests of the forward are not repeated.
+    const uint32_t* cm_in = contrib_masks + (((size_t)(range.x >> 5) + tile) * 8 + warp) * 32
+                            + ((GS::block_y(g) + l / GS::BW) * 8 + GS::block_x(g) + l % GS::BW);
     uint32_t next_mask = __ldg(cm_in + (size_t)(nb - 1) * SR_CONTRIB_STAGE_WORDS);
+    constexpr uint32_t GMASK = GS::GL == 32 ? 0xffffffffu : ((1u << GS::GL) - 1u);
 
     for (int k = 0; k < nb; k++) {
         const int b = nb - 1 - k, s = k % NST;
-        uint32_t mym = next_mask;
+        const uint32_t own = next_mask;                       // instances of this stage that reached MY pixel
         if (b > 0) next_mask = __ldg(cm_in + (size_t)(b - 1) * SR_CONTRIB_STAGE_WORDS);   // lands during this stage
-        if (!__any_sync(0xffffffffu, mym != 0u)) {
-            // nothing of this stage reached any pixel of the sub-tile: recycle its slot without touching it
-            mbar_wait(&bar[s], (uint32_t)((k / NST) & 1));
-            if (lane == 0 && k + NST < nb) issue(k + NST);
-            continue;
-        }
+        uint32_t mym = own;                                   // ... that reached any pixel of my group
+#pragma unroll
+        for (int o = GS::GL / 2; o > 0; o >>= 1) mym |= __shfl_xor_sync(0xffffffffu, mym, o);
         mbar_wait(&bar[s], (uint32_t)((k / NST) & 1));
-        const int cnt = min(WB, len - b * WB);
         const float4* S = st[s];
-        uint32_t cull = 0;
-        if (lane < cnt) cull = __float_as_uint(S[lane * REC4 + 4].w);
         while (__any_sync(0xffffffffu, mym != 0u)) {
-            const bool act = mym != 0u;
+            const bool act = mym != 0u;                       // my group still has an instance to visit
             const int jj = act ? 31 - __clz(mym) : 0;
             mym &= ~(1u << jj) | (act ? 0u : 0xffffffffu);
-            const int pos = b * WB + jj;                       // == `contributor` after the decrement
+            const int pos = b * WB + jj;                      // == `contributor` after the decrement
+            const bool contrib = act && ((own >> jj) & 1u);   // ... and it reached MY pixel
             float v[16];
 #pragma unroll
             for (int i = 0; i < 16; i++) v[i] = 0.f;
             float m2x = 0.f, m2y = 0.f;
-            bool contrib = false, lowpass = false;
-            const float rho_cut = cull_rho_cut(__shfl_sync(0xffffffffu, cull, jj));   // warp-uniform, before any divergence
-            if (act && pos < last_contributor) {
+            bool lowpass = false;
+            if (contrib) {
                 const float4 r0 = S[jj * REC4], r1 = S[jj * REC4 + 1], r2 = S[jj * REC4 + 2];
-                // identical geometry / alpha arithmetic to the forward so that the skips agree
+                // identical geometry / alpha arithmetic to the forward
                 const float kx = ff(pixx, r1.z, -r0.x), ky = ff(pixx, r1.w, -r0.y), kz = ff(pixx, r2.x, -r0.z);
                 const float lx_ = ff(pixy, r1.z, -r0.w), ly_ = ff(pixy, r1.w, -r1.x), lz_ = ff(pixy, r2.x, -r1.y);
                 const float pz = ff(kx, ly_, -fm(ky, lx_));
@@ -190,94 +191,101 @@ composite_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
                 const float q2 = ff(dx, dx, fm(dy, dy));
                 const float rho2d = fa(q2, q2);
                 const float rho = fminf(rho3d, rho2d);
-                if (pz != 0.0f && !(rho > rho_cut)) {
-                    const float c_d = (rho3d <= rho2d) ? fa(r2.x, ff(r1.z, sx, fm(r1.w, sy))) : r2.x;
-                    const float power = fm(rho, -0.5f);
-                    const float G = expf(power);
-                    const float alpha = fminf(0.99f, fm(r2.w, G));
-                    if (!(c_d < 0.2f) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f)) {
-                        contrib = true;
-                        const float4 r3 = S[jj * REC4 + 3], r4 = S[jj * REC4 + 4];
-                        // one approximate reciprocal of (1 - alpha) serves the transmittance recurrence and the
-                        // background term (the reference divides twice, IEEE; the difference is ~1 ulp per step)
-                        const float r1ma = rcp_approx(1.f - alpha);
-                        T = T * r1ma;
-                        const float aT = alpha * T;
-                        float dL_dalpha = 0.f;
-                        // colour
-                        dL_dalpha += (r3.w - accum_rec0) * dpix0 + (r4.x - accum_rec1) * dpix1 + (r4.y - accum_rec2) * dpix2;
-                        v[10] = aT * dpix0; v[11] = aT * dpix1; v[12] = aT * dpix2;
-                        // distortion / median
-                        float dL_dz = 0.f, dL_dweight = 0.f;
-                        float m_d, dmd_dd;
-                        map_depth_vg(c_d, m_d, dmd_dd);
-                        if (pos == median_contributor - 1) { dL_dz += dL_dmedian_depth; dL_dweight += dL_dmax_dweight; }
-                        dL_dweight += (final_D2 + m_d * m_d * final_A - 2.f * m_d * final_D) * dL_dreg;
-                        dL_dalpha += dL_dweight - last_dL_dT;
-                        last_dL_dT = dL_dweight * alpha + (1.f - alpha) * last_dL_dT;
-                        const float dL_dmd = 2.0f * aT * (m_d * final_A - final_D) * dL_dreg;
-                        dL_dz += dL_dmd * dmd_dd;
-                        // depth, alpha
-                        dL_dalpha += (c_d - accum_depth_rec) * dL_ddepth;
-                        dL_dalpha += (1.f - accum_alpha_rec) * dL_daccum;
-                        // normal
-                        dL_dalpha += (r3.x - accum_n0) * dn0 + (r3.y - accum_n1) * dn1 + (r3.z - accum_n2) * dn2;
-                        v[13] = aT * dn0; v[14] = aT * dn1; v[15] = aT * dn2;
-                        // fold this contributor into the accumulators the NEXT (nearer) contributor sees
-                        const float oma = 1.f - alpha;
-                        accum_rec0 = alpha * r3.w + oma * accum_rec0;
-                        accum_rec1 = alpha * r4.x + oma * accum_rec1;
-                        accum_rec2 = alpha * r4.y + oma * accum_rec2;
-                        accum_depth_rec = alpha * c_d + oma * accum_depth_rec;
-                        accum_alpha_rec = alpha + oma * accum_alpha_rec;
-                        accum_n0 = alpha * r3.x + oma * accum_n0;
-                        accum_n1 = alpha * r3.y + oma * accum_n1;
-                        accum_n2 = alpha * r3.z + oma * accum_n2;
+                const float c_d = (rho3d <= rho2d) ? fa(r2.x, ff(r1.z, sx, fm(r1.w, sy))) : r2.x;
+                const float power = fm(rho, -0.5f);
+                const float G_ = expf(power);
+                const float alpha = fminf(0.99f, fm(r2.w, G_));
+                const float4 r3 = S[jj * REC4 + 3], r4 = S[jj * REC4 + 4];
+                // one approximate reciprocal of (1 - alpha) serves the transmittance recurrence and the
+                // background term (the reference divides twice, IEEE; the difference is ~1 ulp per step)
+                const float r1ma = rcp_approx(1.f - alpha);
+                T = T * r1ma;
+                const float aT = alpha * T;
+                float dL_dalpha = 0.f;
+                // colour
+                dL_dalpha += (r3.w - accum_rec0) * dpix0 + (r4.x - accum_rec1) * dpix1 + (r4.y - accum_rec2) * dpix2;
+                v[10] = aT * dpix0; v[11] = aT * dpix1; v[12] = aT * dpix2;
+                // distortion / median
+                float dL_dz = 0.f, dL_dweight = 0.f;
+                float m_d, dmd_dd;
+                map_depth_vg(c_d, m_d, dmd_dd);
+                if (pos == median_contributor - 1) { dL_dz += dL_dmedian_depth; dL_dweight += dL_dmax_dweight; }
+                dL_dweight += (final_D2 + m_d * m_d * final_A - 2.f * m_d * final_D) * dL_dreg;
+                dL_dalpha += dL_dweight - last_dL_dT;
+                last_dL_dT = dL_dweight * alpha + (1.f - alpha) * last_dL_dT;
+                const float dL_dmd = 2.0f * aT * (m_d * final_A - final_D) * dL_dreg;
+                dL_dz += dL_dmd * dmd_dd;
+                // depth, alpha
+                dL_dalpha += (c_d - accum_depth_rec) * dL_ddepth;
+                dL_dalpha += (1.f - accum_alpha_rec) * dL_daccum;
+                // normal
+                dL_dalpha += (r3.x - accum_n0) * dn0 + (r3.y - accum_n1) * dn1 + (r3.z - accum_n2) * dn2;
+                v[13] = aT * dn0; v[14] = aT * dn1; v[15] = aT * dn2;
+                // fold this contributor into the accumulators the NEXT (nearer) contributor sees
+                const float oma = 1.f - alpha;
+                accum_rec0 = alpha * r3.w + oma * accum_rec0;
+                accum_rec1 = alpha * r4.x + oma * accum_rec1;
+                accum_rec2 = alpha * r4.y + oma * accum_rec2;
+                accum_depth_rec = alpha * c_d + oma * accum_depth_rec;
+                accum_alpha_rec = alpha + oma * accum_alpha_rec;
+                accum_n0 = alpha * r3.x + oma * accum_n0;
+                accum_n1 = alpha * r3.y + oma * accum_n1;
+                accum_n2 = alpha * r3.z + oma * accum_n2;
 
-                        dL_dalpha *= T;
-                        dL_dalpha += (-T_final * r1ma) * bg_dot_dpixel;
-                        const float dL_dG = r2.w * dL_dalpha;
-                        dL_dz += aT * dL_ddepth;
-                        if (rho3d <= rho2d) {
-                            const float dL_dsx = dL_dG * -G * sx + dL_dz * r1.z;
-                            const float dL_dsy = dL_dG * -G * sy + dL_dz * r1.w;
-                            const float rpz = rcp_approx(pz);
-                            const float dpx = dL_dsx * rpz, dpy = dL_dsy * rpz, dpz = -(dpx * sx + dpy * sy);
-                            // dL_dk = l x dL_dp ; dL_dl = dL_dp x k
-                            const float dkx = ly_ * dpz - lz_ * dpy, dky = lz_ * dpx - lx_ * dpz, dkz = lx_ * dpy - ly_ * dpx;
-                            const float dlx = dpy * kz - dpz * ky, dly = dpz * kx - dpx * kz, dlz = dpx * ky - dpy * kx;
-                            v[0] = -dkx; v[1] = -dky; v[2] = -dkz;
-                            v[3] = -dlx; v[4] = -dly; v[5] = -dlz;
-                            v[6] = pixx * dkx + pixy * dlx + dL_dz * sx;
-                            v[7] = pixx * dky + pixy * dly + dL_dz * sy;
-                            v[8] = pixx * dkz + pixy * dlz + dL_dz;
-                        } else {
-                            lowpass = true;
-                            m2x = dL_dG * (-G * 2.0f * dx);
-                            m2y = dL_dG * (-G * 2.0f * dy);
-                            v[8] = dL_dz;
-                        }
-                        v[9] = G * dL_dalpha;
+                dL_dalpha *= T;
+                dL_dalpha += (-T_final * r1ma) * bg_dot_dpixel;
+                const float dL_dG = r2.w * dL_dalpha;
+                dL_dz += aT * dL_ddepth;
+                if (rho3d <= rho2d) {
+                    const float dL_dsx = dL_dG * -G_ * sx + dL_dz * r1.z;
+                    const float dL_dsy = dL_dG * -G_ * sy + dL_dz * r1.w;
+                    const float rpz = rcp_approx(pz);
+                    const float dpx = dL_dsx * rpz, dpy = dL_dsy * rpz, dpz = -(dpx * sx + dpy * sy);
+                    // dL_dk = l x dL_dp ; dL_dl = dL_dp x k
+                    const float dkx = ly_ * dpz - lz_ * dpy, dky = lz_ * dpx - lx_ * dpz, dkz = lx_ * dpy - ly_ * dpx;
+                    const float dlx = dpy * kz - dpz * ky, dly = dpz * kx - dpx * kz, dlz = dpx * ky - dpy * kx;
+                    v[0] = -dkx; v[1] = -dky; v[2] = -dkz;
+                    v[3] = -dlx; v[4] = -dly; v[5] = -dlz;
+                    v[6] = pixx * dkx + pixy * dlx + dL_dz * sx;
+                    v[7] = pixx * dky + pixy * dly + dL_dz * sy;
+                    v[8] = pixx * dkz + pixy * dlz + dL_dz;
+                } else {
+                    lowpass = true;
+                    m2x = dL_dG * (-G_ * 2.0f * dx);
+                    m2y = dL_dG * (-G_ * 2.0f * dy);
+                    v[8] = dL_dz;
+                }
+                v[9] = G_ * dL_dalpha;
+            }
+            if constexpr (GS::GL == 1) {
+                // one pixel per group: nothing to reduce, the lane's 16 components leave as four vector reductions
+                if (contrib) {
+                    float* gp = sgrad + (size_t)__float_as_uint(S[jj * REC4 + 4].z) * SR_GRAD_FLOATS;
+                    red_add<16>(gp, v);
+                    if (lowpass) {
+                        const float w2[16] = {m2x, m2y};
+                        red_add<2>(gp + SR_G_M2D, w2);
                     }
                 }
-            }
-            const uint32_t cb = __ballot_sync(0xffffffffu, contrib);
-            if (cb) {
-                // this lane's group has a contributor?  (its REDs are skipped otherwise; the shuffles are warp-wide)
-                const bool gact = (cb >> (g * GS::GL)) & (GS::GL == 32 ? 0xffffffffu : ((1u << GS::GL) - 1u));
-                const uint32_t id = __float_as_uint(S[jj * REC4 + 4].z);
-                float* gp = sgrad + (size_t)id * SR_GRAD_FLOATS;
-                butterfly16<GS::GL>(v, lane);
-                constexpr int NV = BflyOut<GS::GL>::NV;
-                const int c0 = comp_base<GS::GL>(lane);
-                if (gact && (GS::GL < 32 || (lane & 1) == 0)) red_add<NV>(gp + c0, v);
-                if (__any_sync(0xffffffffu, lowpass)) {
-                    // 2-value halving butterfly inside the group: its lane 0 ends with sum(m2x), lane GL/2 with sum(m2y)
-                    const bool hi = lane & (GS::GL / 2);
-                    float w = (hi ? m2y : m2x) + __shfl_xor_sync(0xffffffffu, hi ? m2x : m2y, GS::GL / 2);
+            } else {
+                const uint32_t cb = __ballot_sync(0xffffffffu, contrib);
+                if (cb) {
+                    // this lane's group has a contributor?  (its REDs are skipped otherwise; the shuffles are warp-wide)
+                    const bool gact = (cb >> (g * GS::GL)) & GMASK;
+                    const uint32_t id = __float_as_uint(S[jj * REC4 + 4].z);
+                    float* gp = sgrad + (size_t)id * SR_GRAD_FLOATS;
+                    butterfly16<GS::GL>(v, lane);
+                    constexpr int NV = BflyOut<GS::GL>::NV;
+                    const int c0 = comp_base<GS::GL>(lane);
+                    if (gact && (GS::GL < 32 || (lane & 1) == 0)) red_add<NV>(gp + c0, v);
+                    if (__any_sync(0xffffffffu, lowpass)) {
+                        // 2-value halving butterfly inside the group: its lane 0 ends with sum(m2x), lane GL/2 with sum(m2y)
+                        const bool hi = lane & (GS::GL / 2);
+                        float w = (hi ? m2y : m2x) + __shfl_xor_sync(0xffffffffu, hi ? m2x : m2y, GS::GL / 2);
 #pragma unroll
-                    for (int o = GS::GL / 4; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
-                    if (gact && (l & (GS::GL / 2 - 1)) == 0) atomicAdd(gp + SR_G_M2D + (l >= GS::GL / 2 ? 1 : 0), w);
+                        for (int o = GS::GL / 4; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+                        if (gact && (l & (GS::GL / 2 - 1)) == 0) atomicAdd(gp + SR_G_M2D + (l >= GS::GL / 2 ? 1 : 0), w);
+                    }
                 }
             }
         }
@@ -300,12 +308,23 @@ cudaError_t launch_composite_bwd(const BwdArgs& a) {
             (const uint32_t*)(a.img + a.il.tile_last), a.dL_dcolor, a.dL_dothers,
             (const uint32_t*)(a.bin + a.bl.contrib), (float*)(a.geom + a.gl.sgrad));
     };
-    switch (comp::groups_from_env()) {
+    // the forward stores per-PIXEL contribution masks, so the backward's grouping is independent of the forward's
+    const int G = comp::bwd_groups_from_env();
+    switch (G) {
         case 1: launch(composite_bwd_kernel<1>); break;
         case 2: launch(composite_bwd_kernel<2>); break;
         case 4: launch(composite_bwd_kernel<4>); break;
+        case 16: launch(composite_bwd_kernel<16>); break;
+        case 32: {
+            // register target: 20 CTAs/SM -> 78 registers, 28 -> 71 (no spills, 0.186 -> 0.181 ms), 32 -> 64 with spills (0.201)
+            static const int occ = [] { const char* e = getenv("SURFEL_BWD_OCC"); return e ? atoi(e) : 28; }();
+            if (occ == 20) launch(composite_bwd_kernel<32, 20>);
+            else if (occ == 32) launch(composite_bwd_kernel<32, 32>);
+            else launch(composite_bwd_kernel<32, 28>);
+            break;
+        }
         default: {
-            // CTAs/SM the register allocation targets: 24 -> 80 registers with 15 spilled values reloaded on every
+            // CTAs/SM the register allocation targets: 24 -> 80 registers with spilled values reloaded on every
             // contributing iteration; 20 -> 96 registers, no spills: 0.372 -> 0.337 ms on the headline frame (16: 0.342)
             static const int occ = [] { const char* e = getenv("SURFEL_BWD_OCC"); return e ? atoi(e) : 20; }();
             if (occ == 24) launch(composite_bwd_kernel<8, 24>);

@@ -71,10 +71,11 @@ composite_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
     float dist1 = 0.f, dist2 = 0.f, distortion = 0.f, median_depth = 0.f, median_weight = 0.f;
     uint32_t median_contributor = 0, last_contributor = 0;
     bool done = !inside;
-    // instances of the current stage that contributed to this lane's pixel; OR-ed over the group at the end of the
-    // stage and kept for the backward (common.cuh bin_layout: contrib)
+    // instances of the current stage that contributed to this lane's pixel, kept for the backward (common.cuh
+    // bin_layout: contrib); slot = pixel index inside the 8x4 sub-tile, so a warp's 32 words are one 128-B store
     uint32_t cmask = 0u;
-    uint32_t* cm_out = contrib_masks + (((size_t)(range.x >> 5) + tile) * 8 + warp) * 8 + g;
+    uint32_t* cm_out = contrib_masks + (((size_t)(range.x >> 5) + tile) * 8 + warp) * 32
+                       + ((by0 - sy0 + l / GS::BW) * 8 + (bx0 - sx0 + l % GS::BW));
 
     for (int b = 0; b < nb; b++) {
         const int s = b % NST;
@@ -142,9 +143,7 @@ composite_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
             cmask |= 1u << jj;
         }
         __syncwarp();                                   // every lane is done reading stage s
-#pragma unroll
-        for (int o = GS::GL / 2; o > 0; o >>= 1) cmask |= __shfl_xor_sync(0xffffffffu, cmask, o);
-        if (l == 0) cm_out[(size_t)b * SR_CONTRIB_STAGE_WORDS] = cmask;
+        cm_out[(size_t)b * SR_CONTRIB_STAGE_WORDS] = cmask;
         cmask = 0u;
         if (__all_sync(0xffffffffu, done)) {
             // drain the copies still in flight before this warp (and its CTA's smem) goes away
@@ -197,6 +196,8 @@ cudaError_t launch_composite_fwd(const FwdArgs& a) {
         case 1: launch(composite_fwd_kernel<1>); break;
         case 2: launch(composite_fwd_kernel<2>); break;
         case 4: launch(composite_fwd_kernel<4>); break;
+        case 16: launch(composite_fwd_kernel<16>); break;
+        case 32: launch(composite_fwd_kernel<32>); break;
         default: launch(composite_fwd_kernel<8>); break;
     }
     sr_count_launch();

@@ -6,11 +6,13 @@
 //   * work item = (tile, 8x4 sub-tile) = one warp = one CTA, launched longest-tile-first; each warp streams the
 //     tile's sorted instance records (80 B each, contiguous) through its own double-buffered shared-memory ring
 //     with cp.async.bulk (TMA 1-D) on its own mbarriers -- no CTA-wide synchronisation;
-//   * the warp is split into G groups of 32/G lanes, each owning a small pixel block of the sub-tile (G=4: 4x2).
-//     Per 32-record stage, lane = instance tests the instance's conservative cull rectangle against every group's
-//     block (G ballots); then each GROUP walks its own survivor list, so up to G different instances are evaluated
-//     per warp iteration.  With ~5x5-pixel footprints this halves the (pixel, instance) evaluations of a
-//     whole-warp 8x4 block (0.99 M -> 0.51 M warp-iterations per headline frame);
+//   * the warp is split into G groups of 32/G lanes, each owning a small pixel block of the sub-tile (default G=32:
+//     one pixel per lane).  Per 32-record stage, lane = instance tests the instance's conservative cull rectangle
+//     against the block columns and rows (8 + 4 ballots for G=32); then each group walks its own survivor list, so up
+//     to G different instances are evaluated per warp iteration.  With ~5x5-pixel footprints a whole-warp 8x4 block
+//     wastes most lanes; a finer block never needs more iterations than a coarser one;
+//   * per stage and pixel the kernel records which instances contributed (one 128-B store per warp): the backward
+//     walks exactly those;
 //   * culling and the rho_cut early-out never change a result: a skipped pair provably has alpha < 1/255;
 //   * per-pair arithmetic uses explicit-rounding intrinsics in the contraction pattern of the reference's
 //     sm_100a SASS, so colour/depth/alpha/normal/median planes are bit-identical to the reference build.

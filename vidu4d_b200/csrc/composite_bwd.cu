@@ -16,9 +16,9 @@
 namespace {
 using namespace comp;
 
-// Recursive-halving sum of v[0..15] over each group of GL lanes (GL = 32, 16, 8 or 4).  Every step exchanges half
+// Recursive-halving sum of v[0..15] over each group of GL lanes (GL = 32, 16, 8, 4 or 2).  Every step exchanges half
 // of the still-live values with the lane `off` away; afterwards a lane holds NV = max(1, 32/GL ... ) totals:
-//   GL=32 or 16: 1 value,  GL=8: 2 values,  GL=4: 4 values, of components  base(lane) + i,  i < NV  (see comp_base).
+//   GL=32 or 16: 1 value,  GL=8: 2,  GL=4: 4,  GL=2: 8 values, of components  base(lane) + i,  i < NV  (see comp_base).
 template <int GL>
 __device__ __forceinline__ void butterfly16(float (&v)[16], int lane) {
     int n = 16;

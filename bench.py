@@ -472,8 +472,8 @@ def main():
             "preprocess_fwd": P * (40 + 12 * 16) + Vv * 93,
             "scan_block_sums": (P // 256) * 8, "emit_keys": P * 20 + R_inst * 12,
             "sort_histogram": R_inst * 8, "sort_plan": 6 * 256 * 8, "onesweep_passes": R_inst * 24 * 6,
-            "ranges_gather": R_inst * (12 + 80 + 80), "composite_fwd": R_inst * 88 + N * 64,
-            "composite_bwd": R_inst * 88 + N * 64 + Vv * 72, "surfel_bwd": Vv * (343 + 240),
+            "ranges_gather": R_inst * (12 + 80 + 80), "composite_fwd": R_inst * 112 + N * 64,
+            "composite_bwd": R_inst * 112 + N * 64 + Vv * 72, "surfel_bwd": Vv * (343 + 240),
         }
         kernels = {}
         for k, v in prof.items():

@@ -37,6 +37,8 @@ _sync_mode = True          # True: read num_rendered back after every forward (l
 _pending: list = []        # nosync mode: (pinned host word, key, capacity) awaiting check_overflow()
 _host_pool: list = []      # pinned uint32[2] words, pre-allocated so that a forward never allocates pinned memory
 _host_next = 0             #   (cudaHostAlloc is illegal during CUDA-graph capture)
+# The module state above belongs to the (single) thread that issues forwards; autograd's backward thread only calls
+# rasterize_gaussians_backward, which touches none of it.
 
 
 def set_sync_mode(flag: bool):
@@ -56,7 +58,7 @@ def _pick_capacity(key, P: int) -> int:
     r = _cap_hint.get(key)
     if r is None:
         return _round_cap(max(4 * P, 4096))
-    return _round_cap(int(r * 1.5) + 4096)     # headroom for frame-to-frame growth in nosync mode (104 B / instance)
+    return _round_cap(int(r * 1.5) + 4096)     # headroom for frame-to-frame growth in nosync mode (136 B / instance)
 
 
 _bytes_to_cap: dict = {}
@@ -103,7 +105,7 @@ def check_overflow(keep: bool = False):
     keep=True leaves the watch list in place (a captured CUDA graph rewrites the same status words on every
     replay: call check_overflow(keep=True) after each replay)."""
     global _host_next
-    bad = None
+    bad, prefilter = None, False
     if _pending:
         torch.cuda.synchronize()
     for host, key, cap in _pending:
@@ -114,9 +116,13 @@ def check_overflow(keep: bool = False):
             bad = (r, cap)
         if status & _capi.SR_STATUS_OVERFLOW:
             bad = (r, cap)
+        if status & _capi.SR_STATUS_PREFILTER:
+            prefilter = True
     if not keep:
         _pending.clear()
         _host_next = 0
+    if prefilter:
+        raise RuntimeError("Point is filtered although prefiltered is set. This shouldn't happen!")
     if bad:
         raise _capi.SurfelRasterError(
             f"instance buffer overflow (or a tile beyond the shared-memory sort) in nosync mode: num_rendered={bad[0]}, "

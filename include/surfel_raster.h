@@ -83,6 +83,8 @@ typedef struct sr_frame {
 /* ---- buffer sizing (replaces required<GeometryState/ImageState/BinningState>, rasterizer_impl.h:66-72) */
 SR_API size_t sr_geom_bytes(int32_t P);
 SR_API size_t sr_image_bytes(int32_t width, int32_t height);
+/* 136 B per instance of capacity (sort ping/pong, sorted record stream, per-pixel contribution masks kept for the
+ * backward) + 1 KB per 16x16 tile: the SAME (capacity, width, height) must be passed to the backward. */
 SR_API size_t sr_binning_bytes(int64_t capacity /* max instances */, int32_t width, int32_t height);
 
 /*

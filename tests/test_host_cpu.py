@@ -151,3 +151,34 @@ def test_render_twin_on_cpu_reference_glue():
     inner = n[1:-1, 1:-1]
     assert torch.allclose(inner, torch.tensor([0.0, 0.0, -1.0]).expand_as(inner), atol=1e-5)
     assert (n[0] == 0).all() and (n[:, 0] == 0).all()
+
+
+def test_contribution_mask_stage_slots_never_overlap():
+    """common.cuh bin_layout: stage s of tile t (32 instances of its sorted list) keeps its per-pixel contribution
+    masks in slot (range.x >> 5) + t + s of a buffer with (capacity >> 5) + tiles + 1 slots.  The composite kernels rely on
+    those slots being disjoint between tiles and inside the buffer for ANY list lengths (no prefix sum of stage counts
+    is ever computed)."""
+    rng = np.random.default_rng(7)
+    for trial in range(200):
+        tiles = int(rng.integers(1, 400))
+        kind = trial % 4
+        if kind == 0:
+            lens = rng.integers(0, 4, size=tiles)                       # mostly tiny / empty tiles
+        elif kind == 1:
+            lens = rng.integers(0, 3000, size=tiles)
+        elif kind == 2:
+            lens = np.where(rng.random(tiles) < 0.7, 0, rng.integers(1, 100, size=tiles))
+        else:
+            lens = rng.choice([0, 1, 31, 32, 33, 63, 64, 65], size=tiles)
+        start = np.concatenate([[0], np.cumsum(lens)[:-1]])
+        R = int(lens.sum())
+        nslots = (R >> 5) + tiles + 1
+        prev_end = 0
+        for t in range(tiles):
+            if lens[t] == 0:
+                continue
+            base = (int(start[t]) >> 5) + t
+            nst = (int(lens[t]) + 31) // 32
+            assert base >= prev_end, (trial, t)
+            assert base + nst <= nslots, (trial, t)
+            prev_end = base + nst

@@ -182,3 +182,30 @@ def test_contribution_mask_stage_slots_never_overlap():
             assert base >= prev_end, (trial, t)
             assert base + nst <= nslots, (trial, t)
             prev_end = base + nst
+
+
+def test_check_overflow_bookkeeping_without_a_gpu(built, monkeypatch):
+    """nosync mode's once-per-step check: capacity hints follow the largest num_rendered seen, an overflowed or
+    prefilter-violating frame raises, keep=True leaves the watch list for the next CUDA-graph replay."""
+    from vidu4d_b200 import _capi, rasterizer as R
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    saved = (list(R._pending), dict(R._cap_hint), R._host_next)
+    try:
+        R._pending.clear(); R._cap_hint.clear()
+        key = (0, 64, 64)
+        R._pending.append((torch.tensor([1000, 0], dtype=torch.int32), key, 4096))
+        R._pending.append((torch.tensor([3000, 0], dtype=torch.int32), key, 4096))
+        R.check_overflow(keep=True)
+        assert R._cap_hint[key] == 3000 and len(R._pending) == 2
+        R.check_overflow()
+        assert not R._pending and R._host_next == 0
+        assert R._pick_capacity(key, 10) == R._round_cap(int(3000 * 1.5) + 4096)
+        R._pending.append((torch.tensor([9000, _capi.SR_STATUS_OVERFLOW], dtype=torch.int32), key, 4096))
+        with pytest.raises(_capi.SurfelRasterError, match="overflow"):
+            R.check_overflow()
+        assert R._cap_hint[key] == 9000 and not R._pending          # hints updated: the re-run will fit
+        R._pending.append((torch.tensor([10, _capi.SR_STATUS_PREFILTER], dtype=torch.int32), key, 4096))
+        with pytest.raises(RuntimeError, match="prefiltered"):
+            R.check_overflow()
+    finally:
+        R._pending[:] = saved[0]; R._cap_hint.clear(); R._cap_hint.update(saved[1]); R._host_next = saved[2]

@@ -197,7 +197,9 @@ int sr_forward(const sr_frame* f, const float* background, const float* means3D,
         CK(launch_ranges_gather(a), "ranges_gather"); DBG("ranges_gather");
         CK(launch_tile_order(a), "tile_order"); DBG("tile_order");
     }
-    CK(launch_composite_fwd(a), "composite_fwd"); DBG("composite_fwd");
+    if (sr_composite_tile_mode()) { CK(launch_composite_tile_fwd(a), "composite_tile_fwd"); }
+    else { CK(launch_composite_fwd(a), "composite_fwd"); }
+    DBG("composite_fwd");
     if (num_rendered_host)
         CK(cudaMemcpyAsync(num_rendered_host, num_rendered_dev, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream), "copy(num_rendered)");
     return 0;
@@ -232,7 +234,9 @@ int sr_backward(const sr_frame* f, const float* background, const float* means3D
     a.dL_dmeans2D = dL_dmeans2D; a.dL_dcolors = dL_dcolors; a.dL_dopacity = dL_dopacity; a.dL_dmeans3D = dL_dmeans3D;
     a.dL_dtransMat = dL_dtransMat; a.dL_dsh = dL_dsh; a.dL_dscales = dL_dscales; a.dL_drotations = dL_drotations;
     a.stream = stream; a.debug = debug;
-    CK(launch_composite_bwd(a), "composite_bwd"); DBG("composite_bwd");
+    if (sr_composite_tile_mode()) { CK(launch_composite_tile_bwd(a), "composite_tile_bwd"); }
+    else { CK(launch_composite_bwd(a), "composite_bwd"); }
+    DBG("composite_bwd");
     CK(launch_surfel_bwd(a), "surfel_bwd"); DBG("surfel_bwd");
     return 0;
 }

@@ -184,6 +184,9 @@ cudaError_t launch_tile_sort_gather(const FwdArgs& a);    // tile_sort.cu
 cudaError_t launch_composite_fwd(const FwdArgs& a);       // composite_fwd.cu
 cudaError_t launch_composite_bwd(const BwdArgs& a);       // composite_bwd.cu
 cudaError_t launch_surfel_bwd(const BwdArgs& a);          // surfel_bwd.cu
+cudaError_t launch_composite_tile_fwd(const FwdArgs& a);  // composite_tile.cu (one CTA per tile, shared chunk ring)
+cudaError_t launch_composite_tile_bwd(const BwdArgs& a);  // composite_tile.cu
+bool sr_composite_tile_mode();                            // SURFEL_COMPOSITE=tile|warp (default: tile)
 cudaError_t launch_mark_visible(int P, const float* means3D, const float* vm, uint8_t* present, cudaStream_t s);
 
 void sr_count_launch(int n = 1);

@@ -21,7 +21,7 @@
 namespace {
 using namespace comp;
 
-template <int G>
+template <int G, int ABL = 0>
 __global__ void __launch_bounds__(32 * WPC)
 composite_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order, int n_items, int tiles_x,
                      const float4* __restrict__ irec, int W, int H,
@@ -99,7 +99,8 @@ composite_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
             mym &= mym - 1;                              // no-op when mym == 0
             const float rho_cut = cull_rho_cut(__shfl_sync(0xffffffffu, cull, jj));   // before any divergence
             if (!act || done) continue;
-            const float4 r0 = S[jj * REC4], r1 = S[jj * REC4 + 1], r2 = S[jj * REC4 + 2];
+            const int jr = (ABL == 2) ? (jj & 1) : jj;     // ABL (diagnostic): 2 = conflict-free broadcast record loads
+            const float4 r0 = S[jr * REC4], r1 = S[jr * REC4 + 1], r2 = S[jr * REC4 + 2];
             // T rows: Tu=(r0.x,r0.y,r0.z) Tv=(r0.w,r1.x,r1.y) Tw=(r1.z,r1.w,r2.x); xy=(r2.y,r2.z); opac=r2.w
             const float kx = ff(pixx, r1.z, -r0.x), ky = ff(pixx, r1.w, -r0.y), kz = ff(pixx, r2.x, -r0.z);
             const float lx_ = ff(pixy, r1.z, -r0.w), ly_ = ff(pixy, r1.w, -r1.x), lz_ = ff(pixy, r2.x, -r1.y);
@@ -145,7 +146,7 @@ composite_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
             cmask |= 1u << jj;
         }
         __syncwarp();                                   // every lane is done reading stage s
-        cm_out[(size_t)b * SR_CONTRIB_STAGE_WORDS] = cmask;
+        if (ABL != 1 || cmask == 0x12345u) cm_out[(size_t)b * SR_CONTRIB_STAGE_WORDS] = cmask;   // ABL 1: no mask store
         cmask = 0u;
         if (__all_sync(0xffffffffu, done)) {
             // drain the copies still in flight before this warp (and its CTA's smem) goes away
@@ -199,7 +200,13 @@ cudaError_t launch_composite_fwd(const FwdArgs& a) {
         case 2: launch(composite_fwd_kernel<2>); break;
         case 4: launch(composite_fwd_kernel<4>); break;
         case 16: launch(composite_fwd_kernel<16>); break;
-        case 32: launch(composite_fwd_kernel<32>); break;
+        case 32: {
+            static const int abl = [] { const char* e = getenv("SURFEL_FWD_ABL"); return e ? atoi(e) : 0; }();
+            if (abl == 1) launch(composite_fwd_kernel<32, 1>);
+            else if (abl == 2) launch(composite_fwd_kernel<32, 2>);
+            else launch(composite_fwd_kernel<32>);
+            break;
+        }
         default: launch(composite_fwd_kernel<8>); break;
     }
     sr_count_launch();

@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define SR_ABI_VERSION 2
+#define SR_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define SR_API __attribute__((visibility("default")))
@@ -58,13 +58,6 @@ extern "C" {
 #define SR_STATUS_OK        0u
 #define SR_STATUS_OVERFLOW  1u   /* num_rendered > capacity: nothing was binned or composited */
 #define SR_STATUS_PREFILTER 4u   /* prefiltered was set but a surfel was culled (the reference __trap()s) */
-#define SR_STATUS_SORT_CAP  8u   /* SR_FLAG_LOCAL_SORT: a tile holds more instances than the shared-memory sort takes;
-                                    nothing was composited -- call again without the flag */
-
-/* sr_frame.flags */
-#define SR_FLAG_LOCAL_SORT  1u   /* bin by tile with atomics, sort each tile's (depth, id) list in shared memory
-                                    (same order as the global stable radix sort: ties are broken by surfel id, which is
-                                    the emission order); falls back via SR_STATUS_SORT_CAP */
 
 /* One frame's static description (GaussianRasterizationSettings,
  * RAST/diff_surfel_rasterization/__init__.py:158-170, plus P/M). */
@@ -77,7 +70,7 @@ typedef struct sr_frame {
     float   scale_modifier;  /* accepted and ignored, exactly like the reference (forward.cu:95) */
     int32_t prefiltered;     /* if set, a culled surfel is an error in the reference (__trap); we report it via status bit 2 */
     int32_t debug;           /* if set, synchronise + check after every launch (auxiliary.h:271-278) */
-    uint32_t flags;          /* SR_FLAG_* */
+    uint32_t flags;          /* reserved, must be 0 */
 } sr_frame;
 
 /* ---- buffer sizing (replaces required<GeometryState/ImageState/BinningState>, rasterizer_impl.h:66-72) */
@@ -121,6 +114,45 @@ SR_API int sr_backward(const sr_frame* f,
                 const float* viewmatrix, const float* projmatrix, const float* campos,
                 const int32_t* radii,
                 const float* dL_dout_color, const float* dL_dout_others,
+                void* geom_buffer, void* binning_buffer, void* image_buffer, int64_t capacity,
+                float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity, float* dL_dmeans3D,
+                float* dL_dtransMat, float* dL_dsh, float* dL_dscales, float* dL_drotations,
+                void* stream);
+
+/*
+ * Batched entry points: M independent frames -- different cameras, and optionally
+ * different surfel sets, as in Stage 3 where every frame rasterizes its own bob-warped copy of the canonical surfels
+ * (lab4d/nnutils/deformable_gaussian.py:1175-1188 loops frames in Python) -- in ONE launch set: every kernel of the
+ * path gets a frame dimension, so a step costs the same ~15 launches whatever M is and the GPU sees M x the CTAs.
+ *
+ * Layout: viewmatrix[M*16], projmatrix[M*16], campos[M*3]; out_color[M*3*H*W], out_others[M*8*H*W], radii[M*P];
+ * geom/binning/image buffers are M consecutive per-frame buffers of sr_*_bytes() each (same capacity for every frame);
+ * num_rendered_dev / num_rendered_host are uint32[M*2] = {num_rendered, status} per frame.  Per-surfel inputs are
+ * addressed as base + frame * stride (in floats; sr_batch), stride 0 = shared by all frames.  background[3] is shared.
+ * Backward: dL_dout_color[M*3*H*W], dL_dout_others[M*8*H*W]; every gradient output is written per frame, (M, P, .);
+ * grad_scale (optional DEVICE scalar, NULL = 1) multiplies dL_dout_* -- the upstream scalar of a fused loss.
+ * sr_forward / sr_backward are the M = 1 case.
+ */
+typedef struct sr_batch {
+    int32_t frames;                                   /* M >= 1 */
+    int64_t means3D, shs, colors_precomp, opacities, scales, rotations;   /* floats between consecutive frames; 0 = shared */
+} sr_batch;
+
+SR_API int sr_forward_batch(const sr_frame* f, const sr_batch* b,
+               const float* background, const float* means3D, const float* shs,
+               const float* colors_precomp, const float* opacities, const float* scales,
+               const float* rotations, const float* viewmatrix, const float* projmatrix,
+               const float* campos,
+               float* out_color, float* out_others, int32_t* radii,
+               void* geom_buffer, void* binning_buffer, void* image_buffer, int64_t capacity,
+               uint32_t* num_rendered_dev, uint32_t* num_rendered_host, void* stream);
+
+SR_API int sr_backward_batch(const sr_frame* f, const sr_batch* b,
+                const float* background, const float* means3D, const float* shs,
+                const float* colors_precomp, const float* scales, const float* rotations,
+                const float* viewmatrix, const float* projmatrix, const float* campos,
+                const int32_t* radii,
+                const float* dL_dout_color, const float* dL_dout_others, const float* grad_scale,
                 void* geom_buffer, void* binning_buffer, void* image_buffer, int64_t capacity,
                 float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity, float* dL_dmeans3D,
                 float* dL_dtransMat, float* dL_dsh, float* dL_dscales, float* dL_drotations,

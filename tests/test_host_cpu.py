@@ -188,23 +188,29 @@ def test_check_overflow_bookkeeping_without_a_gpu(built, monkeypatch):
     """nosync mode's once-per-step check: capacity hints follow the largest num_rendered seen, an overflowed or
     prefilter-violating frame raises, keep=True leaves the watch list for the next CUDA-graph replay."""
     from vidu4d_b200 import _capi, rasterizer as R
-    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    class _Stream:                      # stands in for the torch.cuda.Stream a forward ran on
+        synced = 0
+
+        def synchronize(self):
+            _Stream.synced += 1
+    st = _Stream()
     saved = (list(R._pending), dict(R._cap_hint), R._host_next)
     try:
         R._pending.clear(); R._cap_hint.clear()
         key = (0, 64, 64)
-        R._pending.append((torch.tensor([1000, 0], dtype=torch.int32), key, 4096))
-        R._pending.append((torch.tensor([3000, 0], dtype=torch.int32), key, 4096))
+        R._pending.append((torch.tensor([[1000, 0]], dtype=torch.int32), key, 4096, st))
+        R._pending.append((torch.tensor([[500, 0], [3000, 0], [2000, 0]], dtype=torch.int32), key, 4096, st))   # a batch of 3 frames
         R.check_overflow(keep=True)
         assert R._cap_hint[key] == 3000 and len(R._pending) == 2
+        assert _Stream.synced == 2           # every pending forward's own stream is synchronised, not "the current device"
         R.check_overflow()
         assert not R._pending and R._host_next == 0
         assert R._pick_capacity(key, 10) == R._round_cap(int(3000 * 1.5) + 4096)
-        R._pending.append((torch.tensor([9000, _capi.SR_STATUS_OVERFLOW], dtype=torch.int32), key, 4096))
+        R._pending.append((torch.tensor([[100, 0], [9000, _capi.SR_STATUS_OVERFLOW]], dtype=torch.int32), key, 4096, st))
         with pytest.raises(_capi.SurfelRasterError, match="overflow"):
             R.check_overflow()
         assert R._cap_hint[key] == 9000 and not R._pending          # hints updated: the re-run will fit
-        R._pending.append((torch.tensor([10, _capi.SR_STATUS_PREFILTER], dtype=torch.int32), key, 4096))
+        R._pending.append((torch.tensor([[10, _capi.SR_STATUS_PREFILTER]], dtype=torch.int32), key, 4096, st))
         with pytest.raises(RuntimeError, match="prefiltered"):
             R.check_overflow()
     finally:

@@ -11,16 +11,14 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libsurfel_raster.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 SR_STATUS_OVERFLOW = 1
 SR_STATUS_PREFILTER = 4
-SR_STATUS_SORT_CAP = 8
-SR_FLAG_LOCAL_SORT = 1
 
 SYMBOLS = (
     "sr_geom_bytes", "sr_image_bytes", "sr_binning_bytes", "sr_forward", "sr_backward",
     "sr_mark_visible", "sr_debug_view", "sr_abi_version", "sr_last_error", "sr_launch_count",
-    "sr_set_profiling", "sr_get_profile", "sr_post_forward", "sr_post_backward",
+    "sr_set_profiling", "sr_get_profile", "sr_post_forward", "sr_post_backward", "sr_forward_batch", "sr_backward_batch",
 )
 
 
@@ -31,6 +29,12 @@ class SrFrame(C.Structure):
         ("tan_fovx", C.c_float), ("tan_fovy", C.c_float), ("scale_modifier", C.c_float),
         ("prefiltered", C.c_int32), ("debug", C.c_int32), ("flags", C.c_uint32),
     ]
+
+
+class SrBatch(C.Structure):
+    """sr_batch: frames + per-frame strides (in floats; 0 = shared by all frames) of the per-surfel inputs."""
+    _fields_ = [("frames", C.c_int32), ("means3D", C.c_int64), ("shs", C.c_int64), ("colors_precomp", C.c_int64),
+                ("opacities", C.c_int64), ("scales", C.c_int64), ("rotations", C.c_int64)]
 
 
 class SrDebugLayout(C.Structure):
@@ -77,6 +81,10 @@ def load():
     lib.sr_forward.argtypes = [C.POINTER(SrFrame)] + [f32p] * 10 + [vp, vp, vp] + [vp, vp, vp, i64, vp, vp, vp]
     lib.sr_backward.restype = C.c_int
     lib.sr_backward.argtypes = [C.POINTER(SrFrame)] + [f32p] * 9 + [vp] + [f32p] * 2 + [vp, vp, vp, i64] + [f32p] * 8 + [vp]
+    lib.sr_forward_batch.restype = C.c_int
+    lib.sr_forward_batch.argtypes = [C.POINTER(SrFrame), C.POINTER(SrBatch)] + [f32p] * 10 + [vp, vp, vp] + [vp, vp, vp, i64, vp, vp, vp]
+    lib.sr_backward_batch.restype = C.c_int
+    lib.sr_backward_batch.argtypes = [C.POINTER(SrFrame), C.POINTER(SrBatch)] + [f32p] * 9 + [vp] + [f32p] * 3 + [vp, vp, vp, i64] + [f32p] * 8 + [vp]
     lib.sr_mark_visible.restype = C.c_int
     lib.sr_mark_visible.argtypes = [i32, f32p, f32p, f32p, vp, vp]
     lib.sr_debug_view.restype = C.c_int

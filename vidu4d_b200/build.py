@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libsurfel_raster.so")
-SOURCES = ["api.cu", "preprocess.cu", "sort.cu", "tile_sort.cu", "composite_fwd.cu", "composite_bwd.cu", "composite_tile.cu", "surfel_bwd.cu",
+SOURCES = ["api.cu", "preprocess.cu", "sort.cu", "composite_fwd.cu", "composite_bwd.cu", "composite_tile.cu", "surfel_bwd.cu",
            "postprocess.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "composite_common.cuh"),
            os.path.join(HERE, "..", "include", "surfel_raster.h")]

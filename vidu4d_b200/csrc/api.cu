@@ -73,6 +73,11 @@ int check_frame(const sr_frame* f) {
 
 void sr_count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
+cudaError_t sr_memset_frames(void* p, size_t pitch, size_t bytes, int frames, cudaStream_t s) {
+    if (frames == 1) return cudaMemsetAsync(p, 0, bytes, s);
+    return cudaMemset2DAsync(p, pitch, 0, bytes, (size_t)frames, s);
+}
+
 namespace {
 std::atomic<bool> g_profiling{false};
 std::mutex g_prof_mu;
@@ -136,26 +141,27 @@ int sr_debug_view(int32_t P, int32_t width, int32_t height, int64_t capacity, sr
     return 0;
 }
 
-int sr_forward(const sr_frame* f, const float* background, const float* means3D, const float* shs,
-               const float* colors_precomp, const float* opacities, const float* scales, const float* rotations,
-               const float* viewmatrix, const float* projmatrix, const float* campos, float* out_color,
-               float* out_others, int32_t* radii, void* geom_buffer, void* binning_buffer, void* image_buffer,
-               int64_t capacity, uint32_t* num_rendered_dev, uint32_t* num_rendered_host, void* stream_) {
+int sr_forward_batch(const sr_frame* f, const sr_batch* b, const float* background, const float* means3D, const float* shs,
+                     const float* colors_precomp, const float* opacities, const float* scales, const float* rotations,
+                     const float* viewmatrix, const float* projmatrix, const float* campos, float* out_color,
+                     float* out_others, int32_t* radii, void* geom_buffer, void* binning_buffer, void* image_buffer,
+                     int64_t capacity, uint32_t* num_rendered_dev, uint32_t* num_rendered_host, void* stream_) {
     (void)projmatrix;   // only feeds dead code in the reference (auxiliary.h:170-172)
     if (int rc = check_frame(f)) return rc;
+    if (!b || b->frames < 1 || b->frames > 65535) return fail(SR_EINVAL, "batch descriptor: frames must be in [1, 65535]");
     cudaStream_t stream = (cudaStream_t)stream_;
     const bool debug = f->debug != 0;
-    const int P = f->P;
+    const int P = f->P, M = b->frames;
     const size_t N = (size_t)f->width * f->height;
     if (!out_color || !out_others || !num_rendered_dev) return fail(SR_EINVAL, "output pointer is NULL");
     if (!background || !viewmatrix || !campos) return fail(SR_EINVAL, "camera / background pointer is NULL");
-    CK(cudaMemsetAsync(num_rendered_dev, 0, 2 * sizeof(uint32_t), stream), "memset(num_rendered)");
+    CK(cudaMemsetAsync(num_rendered_dev, 0, (size_t)M * 2 * sizeof(uint32_t), stream), "memset(num_rendered)");
     if (P == 0) {
         // rasterize_points.cu:106 -- P == 0 short-circuits to zero-filled outputs
-        CK(cudaMemsetAsync(out_color, 0, 3 * N * sizeof(float), stream), "memset(out_color)");
-        CK(cudaMemsetAsync(out_others, 0, 8 * N * sizeof(float), stream), "memset(out_others)");
+        CK(cudaMemsetAsync(out_color, 0, (size_t)M * 3 * N * sizeof(float), stream), "memset(out_color)");
+        CK(cudaMemsetAsync(out_others, 0, (size_t)M * 8 * N * sizeof(float), stream), "memset(out_others)");
         if (num_rendered_host)
-            CK(cudaMemcpyAsync(num_rendered_host, num_rendered_dev, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream), "copy(num_rendered)");
+            CK(cudaMemcpyAsync(num_rendered_host, num_rendered_dev, (size_t)M * 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream), "copy(num_rendered)");
         return 0;
     }
     if (!means3D || !opacities || !scales || !rotations || !radii) return fail(SR_EINVAL, "surfel attribute pointer is NULL");
@@ -164,6 +170,10 @@ int sr_forward(const sr_frame* f, const float* background, const float* means3D,
     if (shs && f->sh_coeffs == 0) return fail(SR_EINVAL, "shs given but sh_coeffs == 0");
     if (!geom_buffer || !binning_buffer || !image_buffer) return fail(SR_EINVAL, "scratch buffer is NULL");
     if (capacity <= 0 || capacity >= (1ll << 30)) return fail(SR_EINVAL, "capacity must be in (0, 2^30)");
+    // 128-bit / 64-bit vector loads: rotations as float4, scales as float2, SH rows as float4 when 3M % 4 == 0
+    if (((uintptr_t)rotations & 15) || ((uintptr_t)scales & 7) || (shs && ((uintptr_t)shs & 15)) ||
+        ((b->rotations * 4) & 15) || ((b->scales * 4) & 7) || ((b->shs * 4) & 15))
+        return fail(SR_EINVAL, "rotations / shs must be 16-byte aligned and scales 8-byte aligned (per frame)");
 
     FwdArgs a{};
     a.cam = make_cam(f, viewmatrix, campos, background);
@@ -177,42 +187,51 @@ int sr_forward(const sr_frame* f, const float* background, const float* means3D,
     a.prefiltered = f->prefiltered;
     a.key_bits = 32 + (int)sr_higher_msb((uint32_t)a.il.tiles);
     a.stream = stream; a.debug = debug;
+    FrameStrides& fs = a.fs;
+    fs.frames = M;
+    fs.geom = (long long)a.gl.total; fs.bin = (long long)a.bl.total; fs.img = (long long)a.il.total; fs.nr = 2 * sizeof(uint32_t);
+    fs.means3D = b->means3D * 4; fs.shs = b->shs * 4; fs.colors = b->colors_precomp * 4; fs.opac = b->opacities * 4;
+    fs.scales = b->scales * 4; fs.rots = b->rotations * 4; fs.vm = 16 * sizeof(float); fs.campos = 3 * sizeof(float);
+    fs.out_color = (long long)(3 * N * sizeof(float)); fs.out_others = (long long)(8 * N * sizeof(float));
+    fs.radii = (long long)P * sizeof(int32_t);
 
-    a.local_sort = (f->flags & SR_FLAG_LOCAL_SORT) ? 1 : 0;
-    CK(cudaMemsetAsync(a.img + a.il.ranges, 0, a.il.total - a.il.ranges, stream), "memset(tile state)");
-    if (a.local_sort) {
-        // tile-local path (tile_sort.cu): per-tile counts -> ranges -> scatter -> shared-memory sort + record stream
-        CK(cudaMemsetAsync(a.bin + a.bl.sort_ctl, 0, SR_CTL_WORDS * 4, stream), "memset(sort ctl)");
-        // the sorted arrays are the "pong" halves: sort_ctl[SR_CTL_SORTED_SEL] = 1 (little-endian low byte)
-        CK(cudaMemsetAsync(a.bin + a.bl.sort_ctl + 4 * SR_CTL_SORTED_SEL, 1, 1, stream), "set(sorted_sel)");
-        CK(launch_preprocess_fwd(a), "preprocess_fwd"); DBG("preprocess_fwd");
-        CK(launch_tile_scan_emit(a), "tile_scan/emit_local"); DBG("tile_scan/emit_local");
-        CK(launch_tile_sort_gather(a), "tile_sort_gather"); DBG("tile_sort_gather");
-    } else {
-        // global path (sort.cu): one memset clears sort control words, digit histograms and look-back status
-        CK(cudaMemsetAsync(a.bin + a.bl.sort_ctl, 0, a.bl.total - a.bl.sort_ctl, stream), "memset(sort state)");
-        CK(launch_preprocess_fwd(a), "preprocess_fwd"); DBG("preprocess_fwd");
-        CK(launch_scan_emit(a), "scan/emit_keys"); DBG("scan/emit_keys");
-        CK(launch_sort(a), "sort"); DBG("sort");
-        CK(launch_ranges_gather(a), "ranges_gather"); DBG("ranges_gather");
-        CK(launch_tile_order(a), "tile_order"); DBG("tile_order");
-    }
+    // per frame: tile state (ranges .. end of the image buffer); sort control words + digit histograms + look-back status
+    CK(sr_memset_frames(a.img + a.il.ranges, a.il.total, a.il.total - a.il.ranges, M, stream), "memset(tile state)");
+    CK(sr_memset_frames(a.bin + a.bl.sort_ctl, a.bl.total, a.bl.total - a.bl.sort_ctl, M, stream), "memset(sort state)");
+    CK(launch_preprocess_fwd(a), "preprocess_fwd"); DBG("preprocess_fwd");
+    CK(launch_scan_emit(a), "scan/emit_keys"); DBG("scan/emit_keys");
+    CK(launch_sort(a), "sort"); DBG("sort");
+    CK(launch_ranges_gather(a), "ranges_gather"); DBG("ranges_gather");
+    CK(launch_tile_order(a), "tile_order"); DBG("tile_order");
     if (sr_composite_tile_mode()) { CK(launch_composite_tile_fwd(a), "composite_tile_fwd"); }
     else { CK(launch_composite_fwd(a), "composite_fwd"); }
     DBG("composite_fwd");
     if (num_rendered_host)
-        CK(cudaMemcpyAsync(num_rendered_host, num_rendered_dev, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream), "copy(num_rendered)");
+        CK(cudaMemcpyAsync(num_rendered_host, num_rendered_dev, (size_t)M * 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream), "copy(num_rendered)");
     return 0;
 }
 
-int sr_backward(const sr_frame* f, const float* background, const float* means3D, const float* shs,
-                const float* colors_precomp, const float* scales, const float* rotations, const float* viewmatrix,
-                const float* projmatrix, const float* campos, const int32_t* radii, const float* dL_dout_color,
-                const float* dL_dout_others, void* geom_buffer, void* binning_buffer, void* image_buffer,
-                int64_t capacity, float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity, float* dL_dmeans3D,
-                float* dL_dtransMat, float* dL_dsh, float* dL_dscales, float* dL_drotations, void* stream_) {
+int sr_forward(const sr_frame* f, const float* background, const float* means3D, const float* shs,
+               const float* colors_precomp, const float* opacities, const float* scales, const float* rotations,
+               const float* viewmatrix, const float* projmatrix, const float* campos, float* out_color,
+               float* out_others, int32_t* radii, void* geom_buffer, void* binning_buffer, void* image_buffer,
+               int64_t capacity, uint32_t* num_rendered_dev, uint32_t* num_rendered_host, void* stream_) {
+    const sr_batch one = {1, 0, 0, 0, 0, 0, 0};
+    return sr_forward_batch(f, &one, background, means3D, shs, colors_precomp, opacities, scales, rotations, viewmatrix,
+                            projmatrix, campos, out_color, out_others, radii, geom_buffer, binning_buffer, image_buffer,
+                            capacity, num_rendered_dev, num_rendered_host, stream_);
+}
+
+int sr_backward_batch(const sr_frame* f, const sr_batch* b, const float* background, const float* means3D, const float* shs,
+                      const float* colors_precomp, const float* scales, const float* rotations, const float* viewmatrix,
+                      const float* projmatrix, const float* campos, const int32_t* radii, const float* dL_dout_color,
+                      const float* dL_dout_others, const float* grad_scale, void* geom_buffer, void* binning_buffer,
+                      void* image_buffer, int64_t capacity, float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity,
+                      float* dL_dmeans3D, float* dL_dtransMat, float* dL_dsh, float* dL_dscales, float* dL_drotations,
+                      void* stream_) {
     (void)projmatrix;
     if (int rc = check_frame(f)) return rc;
+    if (!b || b->frames < 1 || b->frames > 65535) return fail(SR_EINVAL, "batch descriptor: frames must be in [1, 65535]");
     cudaStream_t stream = (cudaStream_t)stream_;
     const bool debug = f->debug != 0;
     if (f->P == 0) return 0;   // rasterize_points.cu:204
@@ -223,22 +242,53 @@ int sr_backward(const sr_frame* f, const float* background, const float* means3D
         return fail(SR_EINVAL, "gradient output pointer is NULL");
     if (shs && !dL_dsh) return fail(SR_EINVAL, "dL_dsh is NULL");
     if (capacity <= 0) return fail(SR_EINVAL, "capacity must be positive");
+    if (((uintptr_t)rotations & 15) || ((uintptr_t)scales & 7) || (shs && ((uintptr_t)shs & 15)) ||
+        ((uintptr_t)dL_drotations & 15) || ((uintptr_t)dL_dscales & 7) || (dL_dsh && ((uintptr_t)dL_dsh & 15)) ||
+        ((b->rotations * 4) & 15) || ((b->scales * 4) & 7) || ((b->shs * 4) & 15))
+        return fail(SR_EINVAL, "rotations / shs (and their gradients) must be 16-byte aligned, scales 8-byte aligned");
 
+    const int P = f->P, M = b->frames;
+    const size_t N = (size_t)f->width * f->height;
     BwdArgs a{};
     a.cam = make_cam(f, viewmatrix, campos, background);
     if (!shs) a.cam.M = 0;
+    a.grad_scale = grad_scale;
     a.means3D = means3D; a.shs = shs; a.colors_precomp = colors_precomp; a.scales = scales; a.rotations = rotations;
     a.radii = radii; a.dL_dcolor = dL_dout_color; a.dL_dothers = dL_dout_others;
     a.geom = (char*)geom_buffer; a.bin = (char*)binning_buffer; a.img = (char*)image_buffer;
-    a.gl = geom_layout(f->P); a.il = image_layout(f->width, f->height); a.bl = bin_layout(capacity, a.il.tiles);
+    a.gl = geom_layout(P); a.il = image_layout(f->width, f->height); a.bl = bin_layout(capacity, a.il.tiles);
     a.dL_dmeans2D = dL_dmeans2D; a.dL_dcolors = dL_dcolors; a.dL_dopacity = dL_dopacity; a.dL_dmeans3D = dL_dmeans3D;
     a.dL_dtransMat = dL_dtransMat; a.dL_dsh = dL_dsh; a.dL_dscales = dL_dscales; a.dL_drotations = dL_drotations;
     a.stream = stream; a.debug = debug;
+    FrameStrides& fs = a.fs;
+    fs.frames = M;
+    fs.geom = (long long)a.gl.total; fs.bin = (long long)a.bl.total; fs.img = (long long)a.il.total; fs.nr = 2 * sizeof(uint32_t);
+    fs.means3D = b->means3D * 4; fs.shs = b->shs * 4; fs.colors = b->colors_precomp * 4; fs.opac = b->opacities * 4;
+    fs.scales = b->scales * 4; fs.rots = b->rotations * 4; fs.vm = 16 * sizeof(float); fs.campos = 3 * sizeof(float);
+    fs.radii = (long long)P * sizeof(int32_t);
+    fs.dcolor = (long long)(3 * N * sizeof(float)); fs.dothers = (long long)(8 * N * sizeof(float));
+    // gradients are written per frame: (M, P, .) each
+    const long long Pl = P;
+    fs.g_m2d = Pl * 3 * 4; fs.g_col = Pl * 3 * 4; fs.g_opac = Pl * 4; fs.g_m3d = Pl * 3 * 4; fs.g_tm = Pl * 9 * 4;
+    fs.g_sh = Pl * a.cam.M * 3 * 4; fs.g_scales = Pl * 2 * 4; fs.g_rots = Pl * 4 * 4;
     if (sr_composite_tile_mode()) { CK(launch_composite_tile_bwd(a), "composite_tile_bwd"); }
     else { CK(launch_composite_bwd(a), "composite_bwd"); }
     DBG("composite_bwd");
     CK(launch_surfel_bwd(a), "surfel_bwd"); DBG("surfel_bwd");
     return 0;
+}
+
+int sr_backward(const sr_frame* f, const float* background, const float* means3D, const float* shs,
+                const float* colors_precomp, const float* scales, const float* rotations, const float* viewmatrix,
+                const float* projmatrix, const float* campos, const int32_t* radii, const float* dL_dout_color,
+                const float* dL_dout_others, void* geom_buffer, void* binning_buffer, void* image_buffer,
+                int64_t capacity, float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity, float* dL_dmeans3D,
+                float* dL_dtransMat, float* dL_dsh, float* dL_dscales, float* dL_drotations, void* stream_) {
+    const sr_batch one = {1, 0, 0, 0, 0, 0, 0};
+    return sr_backward_batch(f, &one, background, means3D, shs, colors_precomp, scales, rotations, viewmatrix, projmatrix,
+                             campos, radii, dL_dout_color, dL_dout_others, nullptr, geom_buffer, binning_buffer, image_buffer,
+                             capacity, dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dtransMat, dL_dsh, dL_dscales,
+                             dL_drotations, stream_);
 }
 
 int sr_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* projmatrix,

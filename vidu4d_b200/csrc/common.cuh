@@ -146,8 +146,22 @@ static inline uint32_t sr_higher_msb(uint32_t n) {
     return msb;
 }
 
+// Batched launches: every kernel of the path processes `frames` independent frames in ONE launch (frame = blockIdx.y, or
+// interleaved into blockIdx.x for the composite kernels so that the longest tiles of ALL frames start first).  The
+// kernels receive frame 0's pointers plus the BYTE distance between consecutive frames of each array (0 = the array
+// is shared by every frame, e.g. the SH coefficients of a Stage-3 batch).
+struct FrameStrides {
+    int frames;
+    long long geom, bin, img, nr;                                        // scratch buffers, {num_rendered, status} words
+    long long means3D, shs, colors, opac, scales, rots, vm, campos;      // inputs
+    long long out_color, out_others, radii;                              // forward outputs
+    long long dcolor, dothers;                                           // backward inputs
+    long long g_m2d, g_col, g_opac, g_m3d, g_tm, g_sh, g_scales, g_rots; // backward outputs
+};
+
 // ---- launchers implemented in the .cu files ------------------------------------------------
 struct FwdArgs {
+    FrameStrides fs;
     CamParams cam;
     const float* means3D; const float* shs; const float* colors_precomp; const float* opacities;
     const float* scales; const float* rotations;
@@ -156,12 +170,13 @@ struct FwdArgs {
     GeomLayout gl; BinLayout bl; ImageLayout il;
     uint32_t* num_rendered_dev;   // [0]=R, [1]=status
     int prefiltered;
-    int local_sort;               // 1: tile-local sort path (tile_sort.cu), 0: global onesweep (sort.cu)
     int key_bits;                 // 32 + getHigherMsb(tiles)
     cudaStream_t stream;
     bool debug;
 };
 struct BwdArgs {
+    FrameStrides fs;
+    const float* grad_scale;      // optional DEVICE scalar multiplying dL_dcolor / dL_dothers (nullptr = 1)
     CamParams cam;
     const float* means3D; const float* shs; const float* colors_precomp;
     const float* scales; const float* rotations; const int* radii;
@@ -179,8 +194,6 @@ cudaError_t launch_scan_emit(const FwdArgs& a);           // preprocess.cu
 cudaError_t launch_sort(const FwdArgs& a);                // sort.cu
 cudaError_t launch_ranges_gather(const FwdArgs& a);       // sort.cu
 cudaError_t launch_tile_order(const FwdArgs& a);          // sort.cu
-cudaError_t launch_tile_scan_emit(const FwdArgs& a);      // tile_sort.cu
-cudaError_t launch_tile_sort_gather(const FwdArgs& a);    // tile_sort.cu
 cudaError_t launch_composite_fwd(const FwdArgs& a);       // composite_fwd.cu
 cudaError_t launch_composite_bwd(const BwdArgs& a);       // composite_bwd.cu
 cudaError_t launch_surfel_bwd(const BwdArgs& a);          // surfel_bwd.cu
@@ -188,6 +201,8 @@ cudaError_t launch_composite_tile_fwd(const FwdArgs& a);  // composite_tile.cu (
 cudaError_t launch_composite_tile_bwd(const BwdArgs& a);  // composite_tile.cu
 bool sr_composite_tile_mode();                            // SURFEL_COMPOSITE=tile|warp (default: tile)
 cudaError_t launch_mark_visible(int P, const float* means3D, const float* vm, uint8_t* present, cudaStream_t s);
+// clears `bytes` at p + f * pitch for every frame f of the batch (one 2-D memset)
+cudaError_t sr_memset_frames(void* p, size_t pitch, size_t bytes, int frames, cudaStream_t s);
 
 void sr_count_launch(int n = 1);
 
@@ -205,6 +220,16 @@ struct ProfileScope {
 
 // ---- small device helpers -----------------------------------------------------------------
 #ifdef __CUDACC__
+// frame f's copy of an array whose frame 0 starts at p (nullptr stays nullptr)
+template <class T>
+__device__ __forceinline__ T* fr(T* p, long long stride_bytes, int f) {
+    return p ? reinterpret_cast<T*>(reinterpret_cast<uintptr_t>(p) + (uintptr_t)((long long)f * stride_bytes)) : p;
+}
+__device__ __forceinline__ CamParams cam_of_frame(CamParams c, const FrameStrides& fs, int f) {
+    c.vm = fr(c.vm, fs.vm, f);
+    c.campos = fr(c.campos, fs.campos, f);
+    return c;
+}
 __device__ __forceinline__ float4 ld_nc_f4(const float4* p) {
     float4 r;
     asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));

@@ -53,7 +53,8 @@ __device__ __forceinline__ int comp_base(int lane) {
 
 template <int G, int MINB = 20, int ABL = 0>
 __global__ void __launch_bounds__(32 * WPC, MINB / WPC)
-composite_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order, int n_items, int tiles_x,
+composite_bwd_kernel(const FrameStrides fs, const float* __restrict__ grad_scale, const uint2* __restrict__ ranges,
+                     const uint32_t* __restrict__ tile_order, int n_items, int tiles_x,
                      const float4* __restrict__ irec, int W, int H,
                      const float* __restrict__ bg, const float* __restrict__ final_Ts,
                      const uint32_t* __restrict__ n_contrib, const uint32_t* __restrict__ sub_last,
@@ -67,8 +68,13 @@ composite_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
     uint64_t* bar = bar_all[threadIdx.x >> 5];
 
     const int lane = threadIdx.x & 31;
-    const int item = blockIdx.x * WPC + (threadIdx.x >> 5);
+    const int f = (int)(blockIdx.x % (unsigned)fs.frames);
+    const int item = (int)(blockIdx.x / (unsigned)fs.frames) * WPC + (threadIdx.x >> 5);
     if (item >= n_items) return;
+    ranges = fr(ranges, fs.img, f); tile_order = fr(tile_order, fs.img, f); irec = fr(irec, fs.bin, f);
+    final_Ts = fr(final_Ts, fs.img, f); n_contrib = fr(n_contrib, fs.img, f); sub_last = fr(sub_last, fs.img, f);
+    dL_dpixels = fr(dL_dpixels, fs.dcolor, f); dL_dothers = fr(dL_dothers, fs.dothers, f);
+    contrib_masks = fr(contrib_masks, fs.bin, f); sgrad = fr(sgrad, fs.geom, f);
     const int warp = item & 7;
     const int tile = (int)tile_order[item >> 3];
     const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
@@ -100,7 +106,7 @@ composite_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
     __syncwarp();
 
     BwdPixel px;
-    px.load(tile_x * SR_TILE + sx0 + lx, tile_y * SR_TILE + sy0 + ly, W, H, bg, final_Ts, n_contrib, dL_dpixels, dL_dothers);
+    px.load(tile_x * SR_TILE + sx0 + lx, tile_y * SR_TILE + sy0 + ly, W, H, bg, final_Ts, n_contrib, dL_dpixels, dL_dothers, grad_scale);
 
     // The forward recorded, per stage and pixel, which instances contributed (common.cuh bin_layout: contrib).  A group
     // walks the union of its pixels' masks -- exactly the instances worth visiting: no cull test, no trimming, and a
@@ -174,12 +180,13 @@ composite_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
 }  // namespace
 
 cudaError_t launch_composite_bwd(const BwdArgs& a) {
-    cudaError_t e = cudaMemsetAsync(a.geom + a.gl.sgrad, 0, (size_t)(a.cam.P > 0 ? a.cam.P : 1) * SR_GRAD_FLOATS * 4, a.stream);
+    cudaError_t e = sr_memset_frames(a.geom + a.gl.sgrad, (size_t)a.fs.geom, (size_t)(a.cam.P > 0 ? a.cam.P : 1) * SR_GRAD_FLOATS * 4,
+                                     a.fs.frames, a.stream);
     if (e != cudaSuccess) return e;
     ProfileScope ps("composite_bwd", a.stream);
     auto launch = [&](auto kern) {
-        kern<<<(a.il.tiles * 8 + comp::WPC - 1) / comp::WPC, 32 * comp::WPC, 0, a.stream>>>(
-            (const uint2*)(a.img + a.il.ranges), (const uint32_t*)(a.img + a.il.tile_order), a.il.tiles * 8, a.il.tiles_x,
+        kern<<<((a.il.tiles * 8 + comp::WPC - 1) / comp::WPC) * a.fs.frames, 32 * comp::WPC, 0, a.stream>>>(
+            a.fs, a.grad_scale, (const uint2*)(a.img + a.il.ranges), (const uint32_t*)(a.img + a.il.tile_order), a.il.tiles * 8, a.il.tiles_x,
             (const float4*)(a.bin + a.bl.inst_rec), a.cam.W, a.cam.H, a.cam.bg,
             (const float*)(a.img + a.il.final_T), (const uint32_t*)(a.img + a.il.n_contrib),
             (const uint32_t*)(a.img + a.il.tile_last), a.dL_dcolor, a.dL_dothers,

@@ -23,7 +23,7 @@ using namespace comp;
 
 template <int G, int ABL = 0>
 __global__ void __launch_bounds__(32 * WPC)
-composite_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order, int n_items, int tiles_x,
+composite_fwd_kernel(const FrameStrides fs, const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order, int n_items, int tiles_x,
                      const float4* __restrict__ irec, int W, int H,
                      const float* __restrict__ bg, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
                      float* __restrict__ out_color, float* __restrict__ out_others, uint32_t* __restrict__ sub_last,
@@ -37,8 +37,13 @@ composite_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
     uint64_t* bar = bar_all[threadIdx.x >> 5];
 
     const int lane = threadIdx.x & 31;
-    const int item = blockIdx.x * WPC + (threadIdx.x >> 5);
+    // frames are interleaved in blockIdx.x: the longest tiles of EVERY frame of the batch start first
+    const int f = (int)(blockIdx.x % (unsigned)fs.frames);
+    const int item = (int)(blockIdx.x / (unsigned)fs.frames) * WPC + (threadIdx.x >> 5);
     if (item >= n_items) return;
+    ranges = fr(ranges, fs.img, f); tile_order = fr(tile_order, fs.img, f); irec = fr(irec, fs.bin, f);
+    final_T = fr(final_T, fs.img, f); n_contrib = fr(n_contrib, fs.img, f); out_color = fr(out_color, fs.out_color, f);
+    out_others = fr(out_others, fs.out_others, f); sub_last = fr(sub_last, fs.img, f); contrib_masks = fr(contrib_masks, fs.bin, f);
     const int warp = item & 7;
     const int tile = (int)tile_order[item >> 3];
     const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
@@ -189,8 +194,8 @@ cudaError_t launch_composite_fwd(const FwdArgs& a) {
     ProfileScope ps("composite_fwd", a.stream);
     const int G = comp::groups_from_env();
     auto launch = [&](auto kern) {
-        kern<<<(a.il.tiles * 8 + comp::WPC - 1) / comp::WPC, 32 * comp::WPC, 0, a.stream>>>(
-            (const uint2*)(a.img + a.il.ranges), (const uint32_t*)(a.img + a.il.tile_order), a.il.tiles * 8, a.il.tiles_x,
+        kern<<<((a.il.tiles * 8 + comp::WPC - 1) / comp::WPC) * a.fs.frames, 32 * comp::WPC, 0, a.stream>>>(
+            a.fs, (const uint2*)(a.img + a.il.ranges), (const uint32_t*)(a.img + a.il.tile_order), a.il.tiles * 8, a.il.tiles_x,
             (const float4*)(a.bin + a.bl.inst_rec), a.cam.W, a.cam.H, a.cam.bg,
             (float*)(a.img + a.il.final_T), (uint32_t*)(a.img + a.il.n_contrib), a.out_color, a.out_others,
             (uint32_t*)(a.img + a.il.tile_last), (uint32_t*)(a.bin + a.bl.contrib));

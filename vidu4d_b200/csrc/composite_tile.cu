@@ -47,7 +47,7 @@ struct TileSmem {
 // ------------------------------------------------------------------------------------------------ forward
 template <int CH, int NSLOT, int MINB>
 __global__ void __launch_bounds__(32 * TWARPS, MINB)
-composite_tile_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order, int tiles_x,
+composite_tile_fwd_kernel(const FrameStrides fs, const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order, int tiles_x,
                           const float4* __restrict__ irec, int W, int H, const float* __restrict__ bg,
                           float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, float* __restrict__ out_color,
                           float* __restrict__ out_others, uint32_t* __restrict__ sub_last,
@@ -62,7 +62,12 @@ composite_tile_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __re
     volatile uint32_t* ctl = rel + NSLOT;      // [0] warps with all 32 pixels finished, [1] first chunk that is NOT requested
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int tile = (int)tile_order[blockIdx.x];
+    // frames are interleaved in blockIdx.x: the longest tiles of EVERY frame of the batch start first
+    const int f = (int)(blockIdx.x % (unsigned)fs.frames);
+    ranges = fr(ranges, fs.img, f); tile_order = fr(tile_order, fs.img, f); irec = fr(irec, fs.bin, f);
+    final_T = fr(final_T, fs.img, f); n_contrib = fr(n_contrib, fs.img, f); out_color = fr(out_color, fs.out_color, f);
+    out_others = fr(out_others, fs.out_others, f); sub_last = fr(sub_last, fs.img, f); contrib_masks = fr(contrib_masks, fs.bin, f);
+    const int tile = (int)tile_order[blockIdx.x / (unsigned)fs.frames];
     const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
     const uint2 range = ranges[tile];
     const int len = (int)(range.y - range.x);
@@ -241,7 +246,8 @@ composite_tile_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __re
 // ------------------------------------------------------------------------------------------------ backward
 template <int CH, int NSLOT, int MINB>
 __global__ void __launch_bounds__(32 * TWARPS, MINB)
-composite_tile_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order, int tiles_x,
+composite_tile_bwd_kernel(const FrameStrides fs, const float* __restrict__ grad_scale, const uint2* __restrict__ ranges,
+                          const uint32_t* __restrict__ tile_order, int tiles_x,
                           const float4* __restrict__ irec, int W, int H, const float* __restrict__ bg,
                           const float* __restrict__ final_Ts, const uint32_t* __restrict__ n_contrib,
                           const uint32_t* __restrict__ sub_last, const float* __restrict__ dL_dpixels,
@@ -256,7 +262,12 @@ composite_tile_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __re
     uint32_t* rel = reinterpret_cast<uint32_t*>(full + NSLOT);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int tile = (int)tile_order[blockIdx.x];
+    const int f = (int)(blockIdx.x % (unsigned)fs.frames);
+    ranges = fr(ranges, fs.img, f); tile_order = fr(tile_order, fs.img, f); irec = fr(irec, fs.bin, f);
+    final_Ts = fr(final_Ts, fs.img, f); n_contrib = fr(n_contrib, fs.img, f); sub_last = fr(sub_last, fs.img, f);
+    dL_dpixels = fr(dL_dpixels, fs.dcolor, f); dL_dothers = fr(dL_dothers, fs.dothers, f);
+    contrib_masks = fr(contrib_masks, fs.bin, f); sgrad = fr(sgrad, fs.geom, f);
+    const int tile = (int)tile_order[blockIdx.x / (unsigned)fs.frames];
     const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
     const uint2 range = ranges[tile];
     const int rlen = (int)(range.y - range.x);
@@ -291,7 +302,7 @@ composite_tile_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __re
 
     BwdPixel px;
     px.load(tile_x * SR_TILE + sx0 + (lane & 7), tile_y * SR_TILE + sy0 + (lane >> 3), W, H, bg, final_Ts, n_contrib,
-            dL_dpixels, dL_dothers);
+            dL_dpixels, dL_dothers, grad_scale);
 
     uint32_t* cm = cm_all + warp * NSTG * 32 + lane;
     const uint32_t* cm_in = contrib_masks + (((size_t)(range.x >> 5) + tile) * 8 + warp) * 32 + lane;
@@ -385,8 +396,8 @@ cudaError_t launch_composite_tile_fwd(const FwdArgs& a) {
     auto launch = [&](auto kern, size_t smem) {
         err = opt_in_smem(kern, smem);
         if (err != cudaSuccess) return;
-        kern<<<a.il.tiles, 32 * TWARPS, smem, a.stream>>>(
-            (const uint2*)(a.img + a.il.ranges), (const uint32_t*)(a.img + a.il.tile_order), a.il.tiles_x,
+        kern<<<a.il.tiles * a.fs.frames, 32 * TWARPS, smem, a.stream>>>(
+            a.fs, (const uint2*)(a.img + a.il.ranges), (const uint32_t*)(a.img + a.il.tile_order), a.il.tiles_x,
             (const float4*)(a.bin + a.bl.inst_rec), a.cam.W, a.cam.H, a.cam.bg,
             (float*)(a.img + a.il.final_T), (uint32_t*)(a.img + a.il.n_contrib), a.out_color, a.out_others,
             (uint32_t*)(a.img + a.il.tile_last), (uint32_t*)(a.bin + a.bl.contrib));
@@ -405,15 +416,16 @@ cudaError_t launch_composite_tile_fwd(const FwdArgs& a) {
 }
 
 cudaError_t launch_composite_tile_bwd(const BwdArgs& a) {
-    cudaError_t e = cudaMemsetAsync(a.geom + a.gl.sgrad, 0, (size_t)(a.cam.P > 0 ? a.cam.P : 1) * SR_GRAD_FLOATS * 4, a.stream);
+    cudaError_t e = sr_memset_frames(a.geom + a.gl.sgrad, (size_t)a.fs.geom, (size_t)(a.cam.P > 0 ? a.cam.P : 1) * SR_GRAD_FLOATS * 4,
+                                     a.fs.frames, a.stream);
     if (e != cudaSuccess) return e;
     ProfileScope ps("composite_bwd", a.stream);
     cudaError_t err = cudaSuccess;
     auto launch = [&](auto kern, size_t smem) {
         err = opt_in_smem(kern, smem);
         if (err != cudaSuccess) return;
-        kern<<<a.il.tiles, 32 * TWARPS, smem, a.stream>>>(
-            (const uint2*)(a.img + a.il.ranges), (const uint32_t*)(a.img + a.il.tile_order), a.il.tiles_x,
+        kern<<<a.il.tiles * a.fs.frames, 32 * TWARPS, smem, a.stream>>>(
+            a.fs, a.grad_scale, (const uint2*)(a.img + a.il.ranges), (const uint32_t*)(a.img + a.il.tile_order), a.il.tiles_x,
             (const float4*)(a.bin + a.bl.inst_rec), a.cam.W, a.cam.H, a.cam.bg,
             (const float*)(a.img + a.il.final_T), (const uint32_t*)(a.img + a.il.n_contrib),
             (const uint32_t*)(a.img + a.il.tile_last), a.dL_dcolor, a.dL_dothers,

@@ -136,13 +136,19 @@ __device__ __forceinline__ void cull_bbox(const float* T, float cx, float cy, fl
 }
 
 __global__ void __launch_bounds__(256)
-preprocess_fwd_kernel(const CamParams c, const float* __restrict__ means3D, const float* __restrict__ shs,
+preprocess_fwd_kernel(const CamParams c_, const FrameStrides fs, const float* __restrict__ means3D, const float* __restrict__ shs,
                       const float* __restrict__ colors_precomp, const float* __restrict__ opacities,
                       const float2* __restrict__ scales, const float4* __restrict__ rotations,
                       int* __restrict__ radii, float4* __restrict__ srec, float* __restrict__ depths,
                       uint32_t* __restrict__ tiles_touched, uint8_t* __restrict__ clamped_out,
-                      uint32_t* __restrict__ block_sums, uint32_t* __restrict__ status, int prefiltered,
-                      uint32_t* __restrict__ tile_count /* tile-local sort: per-tile instance counters, else nullptr */) {
+                      uint32_t* __restrict__ block_sums, uint32_t* __restrict__ status, int prefiltered) {
+    const int f = blockIdx.y;                       // frame of the batch
+    const CamParams c = cam_of_frame(c_, fs, f);
+    means3D = fr(means3D, fs.means3D, f); shs = fr(shs, fs.shs, f); colors_precomp = fr(colors_precomp, fs.colors, f);
+    opacities = fr(opacities, fs.opac, f); scales = fr(scales, fs.scales, f); rotations = fr(rotations, fs.rots, f);
+    radii = fr(radii, fs.radii, f); srec = fr(srec, fs.geom, f); depths = fr(depths, fs.geom, f);
+    tiles_touched = fr(tiles_touched, fs.geom, f); clamped_out = fr(clamped_out, fs.geom, f);
+    block_sums = fr(block_sums, fs.geom, f); status = fr(status, fs.nr, f);
     // The block's SH coefficients (256 x 3M floats, contiguous) are staged in shared memory with coalesced 128-bit
     // loads; each thread then reads its own padded row (stride 3M+1: conflict-free) instead of 48 scalar loads at a
     // 192-byte lane stride.
@@ -248,9 +254,6 @@ preprocess_fwd_kernel(const CamParams c, const float* __restrict__ means3D, cons
                         clamped_out[idx] = (uint8_t)cl;
                         radius_i = ri;
                         touched = area;
-                        if (tile_count != nullptr)
-                            for (uint32_t y = rmin.y; y < rmax.y; y++)
-                                for (uint32_t x = rmin.x; x < rmax.x; x++) atomicAdd(&tile_count[y * (uint32_t)c.tiles_x + x], 1u);
                     }
                 }
             }
@@ -277,7 +280,10 @@ preprocess_fwd_kernel(const CamParams c, const float* __restrict__ means3D, cons
 
 // exclusive scan of block_sums[0..nb) in place; block_sums[nb] = total; publishes R and the overflow flag
 __global__ void __launch_bounds__(1024)
-scan_block_sums_kernel(uint32_t* __restrict__ block_sums, int nb, uint32_t* __restrict__ num_rendered, long long capacity) {
+scan_block_sums_kernel(const FrameStrides fs, uint32_t* __restrict__ block_sums, int nb, uint32_t* __restrict__ num_rendered,
+                       long long capacity) {
+    block_sums = fr(block_sums, fs.geom, (int)blockIdx.x);          // one block per frame
+    num_rendered = fr(num_rendered, fs.nr, (int)blockIdx.x);
     __shared__ uint32_t wtot[32];
     __shared__ uint32_t carry_s;
     if (threadIdx.x == 0) carry_s = 0;
@@ -315,10 +321,14 @@ scan_block_sums_kernel(uint32_t* __restrict__ block_sums, int nb, uint32_t* __re
 // duplicateWithKeys: offsets come from the block prefix + an in-block scan; same emission order as the
 // reference (ascending surfel id, row-major over the tile rectangle) so that the stable sort ties agree.
 __global__ void __launch_bounds__(256)
-emit_keys_kernel(const CamParams c, const float4* __restrict__ srec, const float* __restrict__ depths,
+emit_keys_kernel(const CamParams c, const FrameStrides fs, const float4* __restrict__ srec, const float* __restrict__ depths,
                  const int* __restrict__ radii, const uint32_t* __restrict__ tiles_touched,
                  const uint32_t* __restrict__ block_sums, uint32_t* __restrict__ point_offsets,
                  uint64_t* __restrict__ keys, uint32_t* __restrict__ values, long long capacity) {
+    const int f = blockIdx.y;
+    srec = fr(srec, fs.geom, f); depths = fr(depths, fs.geom, f); radii = fr(radii, fs.radii, f);
+    tiles_touched = fr(tiles_touched, fs.geom, f); block_sums = fr(block_sums, fs.geom, f);
+    point_offsets = fr(point_offsets, fs.geom, f); keys = fr(keys, fs.bin, f); values = fr(values, fs.bin, f);
     const int idx = blockIdx.x * 256 + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t total = block_sums[gridDim.x];
@@ -384,19 +394,16 @@ __global__ void mark_visible_kernel(int P, const float* __restrict__ means3D, co
 cudaError_t launch_preprocess_fwd(const FwdArgs& a) {
     const int nb = a.gl.nblocks;
     const size_t smem = a.colors_precomp ? 0 : (size_t)256 * (3 * a.cam.M + 1) * sizeof(float);
-    static size_t smem_set = 0;     // opt in to > 48 KB dynamic shared memory once (not a stream operation)
-    if (smem > 48 * 1024 && smem > smem_set) {
+    if (smem > 48 * 1024) {   // > 48 KB dynamic shared memory is an opt-in per device context: cheap, not a stream operation
         cudaError_t e = cudaFuncSetAttribute(preprocess_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        smem_set = smem;
     }
     ProfileScope ps("preprocess_fwd", a.stream);
-    preprocess_fwd_kernel<<<nb, 256, smem, a.stream>>>(
-        a.cam, a.means3D, a.shs, a.colors_precomp, a.opacities, (const float2*)a.scales, (const float4*)a.rotations,
+    preprocess_fwd_kernel<<<dim3(nb, a.fs.frames), 256, smem, a.stream>>>(
+        a.cam, a.fs, a.means3D, a.shs, a.colors_precomp, a.opacities, (const float2*)a.scales, (const float4*)a.rotations,
         a.radii, (float4*)(a.geom + a.gl.surfel_rec), (float*)(a.geom + a.gl.depths),
         (uint32_t*)(a.geom + a.gl.tiles_touched), (uint8_t*)(a.geom + a.gl.clamped),
-        (uint32_t*)(a.geom + a.gl.block_sums), a.num_rendered_dev + 1, a.prefiltered,
-        a.local_sort ? (uint32_t*)(a.img + a.il.tile_count) : nullptr);
+        (uint32_t*)(a.geom + a.gl.block_sums), a.num_rendered_dev + 1, a.prefiltered);
     sr_count_launch();
     return cudaGetLastError();
 }
@@ -405,10 +412,10 @@ cudaError_t launch_scan_emit(const FwdArgs& a) {
     const int nb = a.gl.nblocks;
     uint32_t* bs = (uint32_t*)(a.geom + a.gl.block_sums);
     { ProfileScope ps("scan_block_sums", a.stream);
-      scan_block_sums_kernel<<<1, 1024, 0, a.stream>>>(bs, nb, a.num_rendered_dev, (long long)a.bl.capacity); }
+      scan_block_sums_kernel<<<a.fs.frames, 1024, 0, a.stream>>>(a.fs, bs, nb, a.num_rendered_dev, (long long)a.bl.capacity); }
     ProfileScope ps("emit_keys", a.stream);
-    emit_keys_kernel<<<nb, 256, 0, a.stream>>>(
-        a.cam, (const float4*)(a.geom + a.gl.surfel_rec), (const float*)(a.geom + a.gl.depths), a.radii,
+    emit_keys_kernel<<<dim3(nb, a.fs.frames), 256, 0, a.stream>>>(
+        a.cam, a.fs, (const float4*)(a.geom + a.gl.surfel_rec), (const float*)(a.geom + a.gl.depths), a.radii,
         (const uint32_t*)(a.geom + a.gl.tiles_touched), bs, (uint32_t*)(a.geom + a.gl.point_offsets),
         (uint64_t*)(a.bin + a.bl.keys[0]), (uint32_t*)(a.bin + a.bl.values[0]), (long long)a.bl.capacity);
     sr_count_launch(2);

@@ -29,8 +29,10 @@ struct SortPlan {
 };
 
 __global__ void __launch_bounds__(256)
-sort_histogram_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ num_rendered, long long capacity,
-                      SortPlan plan, uint32_t* __restrict__ hist) {
+sort_histogram_kernel(const FrameStrides fs, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ num_rendered,
+                      long long capacity, SortPlan plan, uint32_t* __restrict__ hist) {
+    const int f = blockIdx.y;
+    keys = fr(keys, fs.bin, f); num_rendered = fr(num_rendered, fs.nr, f); hist = fr(hist, fs.bin, f);
     const uint32_t n = num_rendered[0];
     if ((long long)n > capacity) return;
     __shared__ uint32_t sh[SR_SORT_MAX_PASSES * SR_SORT_BINS];
@@ -55,8 +57,10 @@ sort_histogram_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restr
 
 // one block: exclusive-scan each pass's histogram in place, decide which passes are identities
 __global__ void __launch_bounds__(256)
-sort_plan_kernel(uint32_t* __restrict__ hist, uint32_t* __restrict__ ctl, const uint32_t* __restrict__ num_rendered,
-                 long long capacity, SortPlan plan) {
+sort_plan_kernel(const FrameStrides fs, uint32_t* __restrict__ hist, uint32_t* __restrict__ ctl,
+                 const uint32_t* __restrict__ num_rendered, long long capacity, SortPlan plan) {
+    const int f = blockIdx.x;                       // one block per frame
+    hist = fr(hist, fs.bin, f); ctl = fr(ctl, fs.bin, f); num_rendered = fr(num_rendered, fs.nr, f);
     const uint32_t n = num_rendered[0];
     __shared__ uint32_t wsum[8];
     __shared__ int skip_s[SR_SORT_MAX_PASSES];
@@ -91,10 +95,13 @@ sort_plan_kernel(uint32_t* __restrict__ hist, uint32_t* __restrict__ ctl, const 
 }
 
 __global__ void __launch_bounds__(SR_SORT_THREADS)
-onesweep_pass_kernel(uint64_t* __restrict__ keys0, uint64_t* __restrict__ keys1, uint32_t* __restrict__ vals0,
-                     uint32_t* __restrict__ vals1, const uint32_t* __restrict__ hist, uint32_t* __restrict__ ctl,
-                     uint32_t* __restrict__ status, const uint32_t* __restrict__ num_rendered, int pass, int shift,
-                     int bits, int sort_tiles) {
+onesweep_pass_kernel(const FrameStrides fs, uint64_t* __restrict__ keys0, uint64_t* __restrict__ keys1,
+                     uint32_t* __restrict__ vals0, uint32_t* __restrict__ vals1, const uint32_t* __restrict__ hist,
+                     uint32_t* __restrict__ ctl, uint32_t* __restrict__ status, const uint32_t* __restrict__ num_rendered,
+                     int pass, int shift, int bits, int sort_tiles) {
+    const int f = blockIdx.y;
+    keys0 = fr(keys0, fs.bin, f); keys1 = fr(keys1, fs.bin, f); vals0 = fr(vals0, fs.bin, f); vals1 = fr(vals1, fs.bin, f);
+    hist = fr(hist, fs.bin, f); ctl = fr(ctl, fs.bin, f); status = fr(status, fs.bin, f); num_rendered = fr(num_rendered, fs.nr, f);
     if (ctl[SR_CTL_SKIP + pass]) return;
     const uint32_t n = num_rendered[0];
     __shared__ uint64_t keys_s[SR_SORT_TILE];
@@ -217,10 +224,14 @@ onesweep_pass_kernel(uint64_t* __restrict__ keys0, uint64_t* __restrict__ keys1,
 // identifyTileRanges + materialise the per-instance record stream (sorted order, 80 B each) that the
 // composite kernels pull into shared memory with one bulk-async (TMA) copy per chunk.
 __global__ void __launch_bounds__(256)
-ranges_gather_kernel(const uint64_t* __restrict__ keys0, const uint64_t* __restrict__ keys1,
+ranges_gather_kernel(const FrameStrides fs, const uint64_t* __restrict__ keys0, const uint64_t* __restrict__ keys1,
                      const uint32_t* __restrict__ vals0, const uint32_t* __restrict__ vals1,
                      const uint32_t* __restrict__ ctl, const uint32_t* __restrict__ num_rendered, long long capacity,
                      const float4* __restrict__ srec, float4* __restrict__ irec, uint2* __restrict__ ranges, int tiles_x) {
+    const int f = blockIdx.y;
+    keys0 = fr(keys0, fs.bin, f); keys1 = fr(keys1, fs.bin, f); vals0 = fr(vals0, fs.bin, f); vals1 = fr(vals1, fs.bin, f);
+    ctl = fr(ctl, fs.bin, f); num_rendered = fr(num_rendered, fs.nr, f); srec = fr(srec, fs.geom, f);
+    irec = fr(irec, fs.bin, f); ranges = fr(ranges, fs.img, f);
     const uint32_t n = num_rendered[0];
     if ((long long)n > capacity) return;
     const uint32_t i = blockIdx.x * 256 + threadIdx.x;
@@ -264,7 +275,9 @@ ranges_gather_kernel(const uint64_t* __restrict__ keys0, const uint64_t* __restr
 // object-centric frame start first and the many light / empty ones fill the tail (round r1b ncu: SM busy
 // cycles ranged 152K..548K with row-major order).
 __global__ void __launch_bounds__(1024)
-tile_order_kernel(const uint2* __restrict__ ranges, int tiles, uint32_t* __restrict__ order) {
+tile_order_kernel(const FrameStrides fs, const uint2* __restrict__ ranges, int tiles, uint32_t* __restrict__ order) {
+    ranges = fr(ranges, fs.img, (int)blockIdx.x);   // one block per frame
+    order = fr(order, fs.img, (int)blockIdx.x);
     __shared__ uint32_t cnt[33], start[33];
     if (threadIdx.x < 33) cnt[threadIdx.x] = 0;
     __syncthreads();
@@ -312,13 +325,13 @@ cudaError_t launch_sort(const FwdArgs& a) {
     const long long cap = (long long)a.bl.capacity;
     const int hblocks = (int)((cap + 4095) / 4096);
     { ProfileScope ps("sort_histogram", a.stream);
-      sort_histogram_kernel<<<hblocks, 256, 0, a.stream>>>(k0, a.num_rendered_dev, cap, plan, hist); }
+      sort_histogram_kernel<<<dim3(hblocks, a.fs.frames), 256, 0, a.stream>>>(a.fs, k0, a.num_rendered_dev, cap, plan, hist); }
     { ProfileScope ps("sort_plan", a.stream);
-      sort_plan_kernel<<<1, 256, 0, a.stream>>>(hist, ctl, a.num_rendered_dev, cap, plan); }
+      sort_plan_kernel<<<a.fs.frames, 256, 0, a.stream>>>(a.fs, hist, ctl, a.num_rendered_dev, cap, plan); }
     ProfileScope ps("onesweep_passes", a.stream);
     for (int p = 0; p < plan.npass; p++)
-        onesweep_pass_kernel<<<a.bl.sort_tiles, SR_SORT_THREADS, 0, a.stream>>>(
-            k0, k1, v0, v1, hist, ctl, status, a.num_rendered_dev, p, plan.shift[p], plan.bits[p], a.bl.sort_tiles);
+        onesweep_pass_kernel<<<dim3(a.bl.sort_tiles, a.fs.frames), SR_SORT_THREADS, 0, a.stream>>>(
+            a.fs, k0, k1, v0, v1, hist, ctl, status, a.num_rendered_dev, p, plan.shift[p], plan.bits[p], a.bl.sort_tiles);
     sr_count_launch(2 + plan.npass);
     return cudaGetLastError();
 }
@@ -327,8 +340,8 @@ cudaError_t launch_ranges_gather(const FwdArgs& a) {
     const long long cap = (long long)a.bl.capacity;
     const int blocks = (int)((cap + 255) / 256);
     ProfileScope ps("ranges_gather", a.stream);
-    ranges_gather_kernel<<<blocks, 256, 0, a.stream>>>(
-        (const uint64_t*)(a.bin + a.bl.keys[0]), (const uint64_t*)(a.bin + a.bl.keys[1]),
+    ranges_gather_kernel<<<dim3(blocks, a.fs.frames), 256, 0, a.stream>>>(
+        a.fs, (const uint64_t*)(a.bin + a.bl.keys[0]), (const uint64_t*)(a.bin + a.bl.keys[1]),
         (const uint32_t*)(a.bin + a.bl.values[0]), (const uint32_t*)(a.bin + a.bl.values[1]),
         (const uint32_t*)(a.bin + a.bl.sort_ctl), a.num_rendered_dev, cap,
         (const float4*)(a.geom + a.gl.surfel_rec), (float4*)(a.bin + a.bl.inst_rec),
@@ -339,7 +352,7 @@ cudaError_t launch_ranges_gather(const FwdArgs& a) {
 
 cudaError_t launch_tile_order(const FwdArgs& a) {
     ProfileScope ps("tile_order", a.stream);
-    tile_order_kernel<<<1, 1024, 0, a.stream>>>((const uint2*)(a.img + a.il.ranges), a.il.tiles,
+    tile_order_kernel<<<a.fs.frames, 1024, 0, a.stream>>>(a.fs, (const uint2*)(a.img + a.il.ranges), a.il.tiles,
                                                  (uint32_t*)(a.img + a.il.tile_order));
     sr_count_launch();
     return cudaGetLastError();

@@ -46,13 +46,21 @@ surfel_bwd_body(const CamParams& c, const int idx, const int M, float* osh, cons
 constexpr int SB = 128;
 
 __global__ void __launch_bounds__(SB)
-surfel_bwd_kernel(const CamParams c, const float* __restrict__ means3D, const float* __restrict__ shs,
+surfel_bwd_kernel(const CamParams c_, const FrameStrides fs, const float* __restrict__ means3D, const float* __restrict__ shs,
                   const float2* __restrict__ scales, const float4* __restrict__ rotations, const int* __restrict__ radii,
                   const float4* __restrict__ srec, const uint8_t* __restrict__ clamped, const float4* __restrict__ sgrad,
                   float* __restrict__ dL_dmeans2D, float* __restrict__ dL_dcolors, float* __restrict__ dL_dopacity,
                   float* __restrict__ dL_dmeans3D, float* __restrict__ dL_dtransMat, float* __restrict__ dL_dsh,
                   float2* __restrict__ dL_dscales, float4* __restrict__ dL_drotations) {
     extern __shared__ float shbuf[];
+    const int f = blockIdx.y;                       // frame of the batch
+    const CamParams c = cam_of_frame(c_, fs, f);
+    means3D = fr(means3D, fs.means3D, f); shs = fr(shs, fs.shs, f); scales = fr(scales, fs.scales, f);
+    rotations = fr(rotations, fs.rots, f); radii = fr(radii, fs.radii, f); srec = fr(srec, fs.geom, f);
+    clamped = fr(clamped, fs.geom, f); sgrad = fr(sgrad, fs.geom, f);
+    dL_dmeans2D = fr(dL_dmeans2D, fs.g_m2d, f); dL_dcolors = fr(dL_dcolors, fs.g_col, f); dL_dopacity = fr(dL_dopacity, fs.g_opac, f);
+    dL_dmeans3D = fr(dL_dmeans3D, fs.g_m3d, f); dL_dtransMat = fr(dL_dtransMat, fs.g_tm, f); dL_dsh = fr(dL_dsh, fs.g_sh, f);
+    dL_dscales = fr(dL_dscales, fs.g_scales, f); dL_drotations = fr(dL_drotations, fs.g_rots, f);
     const int M = c.M, M3 = 3 * c.M, stride = M3 + 1;
     const int idx = blockIdx.x * SB + threadIdx.x;
     const int base = blockIdx.x * SB;
@@ -269,15 +277,13 @@ surfel_bwd_body(const CamParams& c, const int idx, const int M, float* osh, cons
 cudaError_t launch_surfel_bwd(const BwdArgs& a) {
     const int nb = (a.cam.P + SB - 1) / SB;
     const size_t smem = (size_t)SB * (3 * a.cam.M + 1) * sizeof(float);
-    static size_t smem_set = 0;     // opt in to > 48 KB dynamic shared memory once (not a stream operation)
-    if (smem > 48 * 1024 && smem > smem_set) {
+    if (smem > 48 * 1024) {   // per device context; cheap, not a stream operation
         cudaError_t e = cudaFuncSetAttribute(surfel_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        smem_set = smem;
     }
     ProfileScope ps("surfel_bwd", a.stream);
-    surfel_bwd_kernel<<<nb, SB, smem, a.stream>>>(
-        a.cam, a.means3D, a.shs, (const float2*)a.scales, (const float4*)a.rotations, a.radii,
+    surfel_bwd_kernel<<<dim3(nb, a.fs.frames), SB, smem, a.stream>>>(
+        a.cam, a.fs, a.means3D, a.shs, (const float2*)a.scales, (const float4*)a.rotations, a.radii,
         (const float4*)(a.geom + a.gl.surfel_rec), (const uint8_t*)(a.geom + a.gl.clamped),
         (const float4*)(a.geom + a.gl.sgrad), a.dL_dmeans2D, a.dL_dcolors, a.dL_dopacity, a.dL_dmeans3D,
         a.dL_dtransMat, a.dL_dsh, (float2*)a.dL_dscales, (float4*)a.dL_drotations);

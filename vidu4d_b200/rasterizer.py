@@ -31,11 +31,10 @@ from . import _capi
 # --------------------------------------------------------------------------------------------
 _CAP_ALIGN = 256           # capacities are multiples of this so that bytes -> capacity is invertible
 _cap_hint: dict = {}       # (device index, W, H) -> last seen num_rendered
-_sort_global: set = set()  # keys for which a tile outgrew the shared-memory sort: use the global onesweep path
-_local_sort_default = False  # the tile-local sort (SR_FLAG_LOCAL_SORT) is opt-in: see DESIGN.md section 3.2
 _sync_mode = True          # True: read num_rendered back after every forward (like the reference)
-_pending: list = []        # nosync mode: (pinned host word, key, capacity) awaiting check_overflow()
-_host_pool: list = []      # pinned uint32[2] words, pre-allocated so that a forward never allocates pinned memory
+_pending: list = []        # nosync mode: (pinned host words (frames,2), key, capacity, stream) awaiting check_overflow()
+_MAX_PENDING = 4096        # nosync forwards that may accumulate before check_overflow() is forced
+_host_pool: list = []      # pinned (64,2) int32 status blocks, pre-allocated so that a forward never allocates pinned memory
 _host_next = 0             #   (cudaHostAlloc is illegal during CUDA-graph capture)
 # The module state above belongs to the (single) thread that issues forwards; autograd's backward thread only calls
 # rasterize_gaussians_backward, which touches none of it.
@@ -84,19 +83,25 @@ def _capacity_from_bytes(nbytes: int, W: int, H: int) -> int:
     return cap
 
 
+_HOST_SLOT_FRAMES = 64      # frames one pinned status block can hold
+
+
 def reserve_host_slots(n: int):
     """Pre-allocate pinned status words for the next `n` nosync forwards (needed before CUDA-graph capture)."""
     while len(_host_pool) - _host_next < n:
-        _host_pool.append(torch.zeros((2,), dtype=torch.int32).pin_memory())
+        _host_pool.append(torch.zeros((_HOST_SLOT_FRAMES, 2), dtype=torch.int32).pin_memory())
 
 
-def _host_slot():
+def _host_slot(frames: int = 1):
+    """Pinned {num_rendered, status} words for one (batched) forward: (frames, 2) int32."""
     global _host_next
+    if frames > _HOST_SLOT_FRAMES:
+        return torch.zeros((frames, 2), dtype=torch.int32).pin_memory()
     if _host_next >= len(_host_pool):
-        _host_pool.append(torch.zeros((2,), dtype=torch.int32).pin_memory())
+        _host_pool.append(torch.zeros((_HOST_SLOT_FRAMES, 2), dtype=torch.int32).pin_memory())
     h = _host_pool[_host_next]
     _host_next += 1
-    return h
+    return h[:frames]
 
 
 def check_overflow(keep: bool = False):
@@ -106,18 +111,14 @@ def check_overflow(keep: bool = False):
     replay: call check_overflow(keep=True) after each replay)."""
     global _host_next
     bad, prefilter = None, False
-    if _pending:
-        torch.cuda.synchronize()
-    for host, key, cap in _pending:
-        r, status = int(host[0]), int(host[1])
-        _cap_hint[key] = max(_cap_hint.get(key, 0), r)
-        if status & _capi.SR_STATUS_SORT_CAP:
-            _sort_global.add(key)
-            bad = (r, cap)
-        if status & _capi.SR_STATUS_OVERFLOW:
-            bad = (r, cap)
-        if status & _capi.SR_STATUS_PREFILTER:
-            prefilter = True
+    for host, key, cap, stream in _pending:
+        stream.synchronize()          # the stream (and device) the forward ran on: its D2H copy of the words has landed
+        for r, status in host.tolist():
+            _cap_hint[key] = max(_cap_hint.get(key, 0), r)
+            if status & _capi.SR_STATUS_OVERFLOW:
+                bad = (r, cap)
+            if status & _capi.SR_STATUS_PREFILTER:
+                prefilter = True
     if not keep:
         _pending.clear()
         _host_next = 0
@@ -125,7 +126,7 @@ def check_overflow(keep: bool = False):
         raise RuntimeError("Point is filtered although prefiltered is set. This shouldn't happen!")
     if bad:
         raise _capi.SurfelRasterError(
-            f"instance buffer overflow (or a tile beyond the shared-memory sort) in nosync mode: num_rendered={bad[0]}, "
+            f"instance buffer overflow in nosync mode: num_rendered={bad[0]}, "
             f"capacity={bad[1]}; the frame was not rendered. Hints updated -- re-run the step.")
 
 
@@ -144,7 +145,38 @@ def _f32c(t, name):
         raise RuntimeError(f"{name} must be a CUDA tensor")   # CHECK_INPUT, rasterize_points.cu:27-28
     if t.dtype != torch.float32:
         t = t.float()
-    return t.contiguous()
+    t = t.contiguous()
+    if t.data_ptr() % 16 != 0 and t.numel() != 0:
+        # the kernels use 128-bit loads (rotations, SH rows) and 64-bit loads (scales); a contiguous view at an odd
+        # storage offset (e.g. `rot[1:]`, a slice of a flat parameter buffer) is re-homed; the reference's scalar glm
+        # loads accept such tensors, so must we
+        t = t.clone()
+    return t
+
+
+def _batch_inputs(M: int, **named):
+    """Normalise the per-surfel inputs of a batched call.  Each value is (tensor, trailing shape or None); a tensor is
+    either shared by the M frames (its single-frame shape) or per frame (leading M).  Returns (contiguous float32
+    tensors, per-frame strides in floats: 0 = shared)."""
+    out, strides = {}, {}
+    for name, (t, tail) in named.items():
+        if t is None or t.numel() == 0:
+            out[name], strides[name] = None, 0
+            continue
+        t = _f32c(t, name)
+        base_ndim = 3 if name == "sh" else 2
+        if t.ndim == base_ndim + 1:
+            if t.shape[0] != M:
+                raise RuntimeError(f"{name}: leading dimension {t.shape[0]} != number of frames {M}")
+            strides[name] = int(t[0].numel()) if M > 1 else 0
+        elif t.ndim == base_ndim:
+            strides[name] = 0
+        else:
+            raise RuntimeError(f"{name} must have {base_ndim} (shared) or {base_ndim + 1} (per frame) dimensions")
+        if tail is not None and tuple(t.shape[-len(tail):]) != tail:
+            raise RuntimeError(f"{name} must have trailing dimensions {tail}")
+        out[name] = t
+    return out, strides
 
 
 def _as_float(x) -> float:
@@ -190,11 +222,10 @@ class _CNamespace:
             cap = _pick_capacity(key, P)
             while True:
                 fr = _capi.SrFrame(P, int(degree), M, W, H, _as_float(tan_fovx), _as_float(tan_fovy),
-                                   float(scale_modifier), int(bool(prefiltered)), int(bool(debug)),
-                                   _capi.SR_FLAG_LOCAL_SORT if (_local_sort_default and key not in _sort_global) else 0)
+                                   float(scale_modifier), int(bool(prefiltered)), int(bool(debug)), 0)
                 binning = torch.empty((lib.sr_binning_bytes(cap, W, H),), dtype=torch.uint8, device=dev)
                 nosync = (not _sync_mode) and key in _cap_hint
-                host = _host_slot() if nosync else torch.empty((2,), dtype=torch.int32, pin_memory=True)
+                host = _host_slot() if nosync else torch.empty((1, 2), dtype=torch.int32, pin_memory=True)
                 rc = lib.sr_forward(
                     C.byref(fr), _ptr(background), _ptr(means3D), _ptr(sh), _ptr(colors), _ptr(opacity),
                     _ptr(scales), _ptr(rotations), _ptr(viewmatrix), _ptr(projmatrix), _ptr(campos),
@@ -203,17 +234,16 @@ class _CNamespace:
                     stream.cuda_stream)
                 _capi.check(rc, "sr_forward")
                 if nosync:
-                    _pending.append((host, key, cap))
+                    _pending.append((host, key, cap, stream))
+                    if len(_pending) > _MAX_PENDING:
+                        check_overflow()      # an unchecked backlog must not grow without bound (nor hide dropped frames)
                     num_rendered = -1
                     break
                 stream.synchronize()
-                num_rendered, status = int(host[0]), int(host[1])
+                num_rendered, status = int(host[0, 0]), int(host[0, 1])
                 _cap_hint[key] = max(_cap_hint.get(key, 0), num_rendered) if not _sync_mode else num_rendered
                 if status & _capi.SR_STATUS_PREFILTER:
                     raise RuntimeError("Point is filtered although prefiltered is set. This shouldn't happen!")
-                if status & _capi.SR_STATUS_SORT_CAP:
-                    _sort_global.add(key)          # some tile is too long for the shared-memory sort: global path
-                    continue
                 if status & _capi.SR_STATUS_OVERFLOW:
                     cap = _round_cap(int(num_rendered * 1.1) + 4096)
                     continue
@@ -254,6 +284,114 @@ class _CNamespace:
                     dL_dsh.data_ptr() if M > 0 else None, dL_dscales.data_ptr(), dL_drotations.data_ptr(),
                     torch.cuda.current_stream(dev).cuda_stream)
                 _capi.check(rc, "sr_backward")
+        return dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dtransMat, dL_dsh, dL_dscales, dL_drotations
+
+    # ---- batched entry points: M frames in one launch set -------------------------------------
+    @staticmethod
+    def rasterize_gaussians_batch(background, means3D, colors, opacity, scales, rotations, scale_modifier, viewmatrix,
+                                  projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh, degree, campos,
+                                  prefiltered=False, debug=False):
+        """M frames at once.  viewmatrix / projmatrix (M,4,4), campos (M,3).  Every per-surfel input is either shared by
+        all frames -- the single-frame shape, e.g. means3D (P,3) -- or per frame with a leading M, e.g. (M,P,3) (Stage 3:
+        each frame rasterizes its own warped copy of the surfels).  Returns (num_rendered (list of M ints, or -1 in nosync
+        mode), out_color (M,3,H,W), out_others (M,8,H,W), radii (M,P), geomBuffer, binningBuffer, imgBuffer)."""
+        lib = _capi.load()
+        M = int(viewmatrix.shape[0])
+        if viewmatrix.ndim != 3 or viewmatrix.shape[1:] != (4, 4) or campos.shape != (M, 3):
+            raise RuntimeError("batched cameras: viewmatrix must be (M,4,4) and campos (M,3)")
+        dev = means3D.device
+        H, W = int(image_height), int(image_width)
+        background = _f32c(background, "background"); viewmatrix = _f32c(viewmatrix, "viewmatrix")
+        projmatrix = _f32c(projmatrix, "projmatrix"); campos = _f32c(campos, "campos")
+        ins, strides = _batch_inputs(M, means3D=(means3D, (3,)), sh=(sh, None), colors=(colors, (3,)), opacity=(opacity, (1,)),
+                                     scales=(scales, (2,)), rotations=(rotations, (4,)))
+        means3D, sh, colors, opacity, scales, rotations = (ins[k] for k in ("means3D", "sh", "colors", "opacity", "scales", "rotations"))
+        P = int(means3D.shape[-2])
+        Msh = int(sh.shape[-2]) if sh is not None and sh.numel() != 0 else 0
+        bt = _capi.SrBatch(M, strides["means3D"], strides["sh"], strides["colors"], strides["opacity"], strides["scales"],
+                           strides["rotations"])
+        with torch.cuda.device(dev):
+            out_color = torch.empty((M, 3, H, W), dtype=torch.float32, device=dev)
+            out_others = torch.empty((M, 8, H, W), dtype=torch.float32, device=dev)
+            radii = torch.empty((M, P), dtype=torch.int32, device=dev)
+            geom = torch.empty((M * lib.sr_geom_bytes(P),), dtype=torch.uint8, device=dev)
+            img = torch.empty((M * lib.sr_image_bytes(W, H),), dtype=torch.uint8, device=dev)
+            nr_dev = torch.empty((M, 2), dtype=torch.int32, device=dev)
+            stream = torch.cuda.current_stream(dev)
+            key = (dev.index, W, H)
+            cap = _pick_capacity(key, P)
+            while True:
+                fr = _capi.SrFrame(P, int(degree), Msh, W, H, _as_float(tan_fovx), _as_float(tan_fovy),
+                                   float(scale_modifier), int(bool(prefiltered)), int(bool(debug)), 0)
+                binning = torch.empty((M * lib.sr_binning_bytes(cap, W, H),), dtype=torch.uint8, device=dev)
+                nosync = (not _sync_mode) and key in _cap_hint
+                host = _host_slot(M) if nosync else torch.empty((M, 2), dtype=torch.int32, pin_memory=True)
+                rc = lib.sr_forward_batch(
+                    C.byref(fr), C.byref(bt), _ptr(background), _ptr(means3D), _ptr(sh), _ptr(colors), _ptr(opacity),
+                    _ptr(scales), _ptr(rotations), _ptr(viewmatrix), _ptr(projmatrix), _ptr(campos),
+                    out_color.data_ptr(), out_others.data_ptr(), _ptr(radii), geom.data_ptr(),
+                    binning.data_ptr(), img.data_ptr(), cap, nr_dev.data_ptr(), host.data_ptr(), stream.cuda_stream)
+                _capi.check(rc, "sr_forward_batch")
+                if nosync:
+                    _pending.append((host, key, cap, stream))
+                    num_rendered = -1
+                    break
+                stream.synchronize()
+                num_rendered = [int(v) for v in host[:, 0]]
+                status = 0
+                for v in host[:, 1]:
+                    status |= int(v)
+                _cap_hint[key] = max(_cap_hint.get(key, 0), max(num_rendered)) if not _sync_mode else max(num_rendered)
+                if status & _capi.SR_STATUS_PREFILTER:
+                    raise RuntimeError("Point is filtered although prefiltered is set. This shouldn't happen!")
+                if status & _capi.SR_STATUS_OVERFLOW:
+                    cap = _round_cap(int(max(num_rendered) * 1.1) + 4096)
+                    continue
+                break
+        return num_rendered, out_color, out_others, radii, geom, binning, img
+
+    @staticmethod
+    def rasterize_gaussians_backward_batch(background, means3D, radii, colors, scales, rotations, scale_modifier, viewmatrix,
+                                           projmatrix, tan_fovx, tan_fovy, dL_dout_color, dL_dout_others, sh, degree, campos,
+                                           geomBuffer, binningBuffer, imageBuffer, grad_scale=None, debug=False):
+        """Backward of rasterize_gaussians_batch.  dL_dout_color (M,3,H,W), dL_dout_others (M,8,H,W); grad_scale: optional
+        0-d device tensor multiplying both (the upstream scalar of a fused loss).  Returns the eight gradient tensors, each
+        with a leading M: (M,P,.)."""
+        lib = _capi.load()
+        M = int(viewmatrix.shape[0])
+        dev = means3D.device
+        H, W = int(dL_dout_color.shape[-2]), int(dL_dout_color.shape[-1])
+        background = _f32c(background, "background"); viewmatrix = _f32c(viewmatrix, "viewmatrix")
+        projmatrix = _f32c(projmatrix, "projmatrix"); campos = _f32c(campos, "campos")
+        dL_dout_color = _f32c(dL_dout_color, "dL_dout_color"); dL_dout_others = _f32c(dL_dout_others, "dL_dout_others")
+        ins, strides = _batch_inputs(M, means3D=(means3D, (3,)), sh=(sh, None), colors=(colors, (3,)),
+                                     scales=(scales, (2,)), rotations=(rotations, (4,)))
+        means3D, sh, colors, scales, rotations = (ins[k] for k in ("means3D", "sh", "colors", "scales", "rotations"))
+        P = int(means3D.shape[-2])
+        Msh = int(sh.shape[-2]) if sh is not None and sh.numel() != 0 else 0
+        bt = _capi.SrBatch(M, strides["means3D"], strides["sh"], strides["colors"], 0, strides["scales"], strides["rotations"])
+        with torch.cuda.device(dev):
+            mk = (lambda *s: torch.empty(s, dtype=torch.float32, device=dev)) if P > 0 else \
+                 (lambda *s: torch.zeros(s, dtype=torch.float32, device=dev))
+            dL_dmeans3D, dL_dmeans2D, dL_dcolors = mk(M, P, 3), mk(M, P, 3), mk(M, P, 3)
+            dL_dopacity, dL_dtransMat, dL_dsh = mk(M, P, 1), mk(M, P, 9), mk(M, P, Msh, 3)
+            dL_dscales, dL_drotations = mk(M, P, 2), mk(M, P, 4)
+            if P > 0:
+                cap = _capacity_from_bytes(int(binningBuffer.numel()) // M, W, H)
+                fr = _capi.SrFrame(P, int(degree), Msh, W, H, _as_float(tan_fovx), _as_float(tan_fovy),
+                                   float(scale_modifier), 0, int(bool(debug)), 0)
+                gs = None
+                if grad_scale is not None:
+                    gs = grad_scale.to(device=dev, dtype=torch.float32).reshape(()).contiguous()
+                rc = lib.sr_backward_batch(
+                    C.byref(fr), C.byref(bt), _ptr(background), _ptr(means3D), _ptr(sh), _ptr(colors), _ptr(scales),
+                    _ptr(rotations), _ptr(viewmatrix), _ptr(projmatrix), _ptr(campos), _ptr(radii),
+                    _ptr(dL_dout_color), _ptr(dL_dout_others), gs.data_ptr() if gs is not None else None,
+                    geomBuffer.data_ptr(), binningBuffer.data_ptr(), imageBuffer.data_ptr(), cap,
+                    dL_dmeans2D.data_ptr(), dL_dcolors.data_ptr(), dL_dopacity.data_ptr(), dL_dmeans3D.data_ptr(),
+                    dL_dtransMat.data_ptr(), dL_dsh.data_ptr() if Msh > 0 else None, dL_dscales.data_ptr(),
+                    dL_drotations.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+                _capi.check(rc, "sr_backward_batch")
         return dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dtransMat, dL_dsh, dL_dscales, dL_drotations
 
     @staticmethod
@@ -348,6 +486,72 @@ class _RasterizeGaussians(torch.autograd.Function):
             grad_cov3Ds_precomp = None
         return (grad_means3D, grad_means2D, grad_sh, grad_colors_precomp, grad_opacities, grad_scales,
                 grad_rotations, grad_cov3Ds_precomp, None)
+
+
+class BatchRasterizationSettings(NamedTuple):
+    """GaussianRasterizationSettings for M frames: viewmatrix / projmatrix are (M,4,4), campos is (M,3)."""
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool = False
+    debug: bool = False
+
+
+def _reduce_like(grad, inp):
+    """(M,P,.) per-frame gradient -> the input's shape: inputs shared by all frames get the sum over frames."""
+    if inp is None or inp.numel() == 0:
+        return None
+    return grad if inp.ndim == grad.ndim else grad.sum(dim=0).view(inp.shape)
+
+
+class _RasterizeGaussiansBatch(torch.autograd.Function):
+    """M frames in one launch set (SURVEY.md 8(f) N1).  Inputs are shared (single-frame shape) or per frame (leading M);
+    means2D is (M,P,3) and only receives the densification proxy gradient, as in the single-frame op."""
+
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, rs):
+        num_rendered, color, allmap, radii, geomBuffer, binningBuffer, imgBuffer = _C.rasterize_gaussians_batch(
+            rs.bg, means3D, colors_precomp, opacities, scales, rotations, rs.scale_modifier, rs.viewmatrix, rs.projmatrix,
+            rs.tanfovx, rs.tanfovy, rs.image_height, rs.image_width, sh, rs.sh_degree, rs.campos, rs.prefiltered, rs.debug)
+        ctx.rs = rs
+        ctx.save_for_backward(colors_precomp, means3D, scales, rotations, radii, sh, opacities, geomBuffer, binningBuffer, imgBuffer)
+        ctx.mark_non_differentiable(radii)
+        return color, radii, allmap
+
+    @staticmethod
+    def backward(ctx, grad_color, grad_radii, grad_allmap):
+        rs = ctx.rs
+        colors_precomp, means3D, scales, rotations, radii, sh, opacities, geomBuffer, binningBuffer, imgBuffer = ctx.saved_tensors
+        M = int(rs.viewmatrix.shape[0])
+        H, W = rs.image_height, rs.image_width
+        if grad_color is None:
+            grad_color = torch.zeros((M, 3, H, W), dtype=torch.float32, device=means3D.device)
+        if grad_allmap is None:
+            grad_allmap = torch.zeros((M, 8, H, W), dtype=torch.float32, device=means3D.device)
+        g2d, gcol, gop, g3d, gtm, gsh, gsc, grot = _C.rasterize_gaussians_backward_batch(
+            rs.bg, means3D, radii, colors_precomp, scales, rotations, rs.scale_modifier, rs.viewmatrix, rs.projmatrix,
+            rs.tanfovx, rs.tanfovy, grad_color, grad_allmap, sh, rs.sh_degree, rs.campos, geomBuffer, binningBuffer, imgBuffer,
+            None, rs.debug)
+        return (_reduce_like(g3d, means3D), g2d, _reduce_like(gsh, sh), _reduce_like(gcol, colors_precomp),
+                _reduce_like(gop, opacities), _reduce_like(gsc, scales), _reduce_like(grot, rotations), None)
+
+
+def rasterize_gaussians_batch(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, raster_settings):
+    """Batched twin of rasterize_gaussians: returns (color (M,3,H,W), radii (M,P), allmap (M,8,H,W))."""
+    dev = means3D.device
+    empty = lambda: torch.empty((0,), dtype=torch.float32, device=dev)  # noqa: E731
+    if (shs is None) == (colors_precomp is None):
+        raise Exception('Please provide excatly one of either SHs or precomputed colors!')
+    return _RasterizeGaussiansBatch.apply(means3D, means2D, empty() if shs is None else shs,
+                                          empty() if colors_precomp is None else colors_precomp, opacities, scales, rotations,
+                                          raster_settings)
 
 
 class GaussianRasterizationSettings(NamedTuple):

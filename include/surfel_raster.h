@@ -198,6 +198,25 @@ SR_API int sr_post_backward(int32_t W, int32_t H, float tan_fovx, float tan_fovy
                             const float* g_depth_expected, const float* g_surf_depth, const float* g_surf_normal,
                             float* g_allmap, void* stream);
 
+/*
+ * Stage-3 image losses fused with the render() post-processing, forward and backward in one pass, M frames per call
+ * (SURVEY.md section 8(f) row N1).  Replaces lab4d/engine/model.py:674-692 (masked L1), :649-653 (mask loss), :817-842
+ * (normal + distortion regularisers) on top of gs/gaussian_renderer/__init__.py:121-145 and, optionally, the
+ * learnable-background composite of lab4d/nnutils/deformable_gaussian.py:188-190.
+ *   color[M*3*HW], allmap[M*8*HW] (the rasterizer's outputs), world_view_transform[M*16], target_rgb[M*3*HW];
+ *   vis2d[M*HW] (NULL = all visible), mask_gt[M*HW] (NULL = no mask term), mask_wt[M*HW] (NULL = 1),
+ *   learnable_bkgd[3] (NULL = none).
+ * Writes loss_terms[M*4] = weighted {rgb, mask, normal, dist} per frame (means over the frame's pixels), and the gradient
+ * of their sum: dL_dcolor[M*3*HW], dL_dallmap[M*8*HW] (fully written), dL_dbkgd[M*3] (if non-NULL).
+ * surf_depth_scratch: M*HW floats.
+ */
+SR_API int sr_render_loss_batch(int32_t M, int32_t W, int32_t H, float tan_fovx, float tan_fovy, float depth_ratio,
+                                const float* color, const float* allmap, const float* world_view_transform,
+                                const float* target_rgb, const float* vis2d, const float* mask_gt, const float* mask_wt,
+                                const float* learnable_bkgd, float w_rgb, float w_mask, float lambda_normal, float lambda_dist,
+                                float* loss_terms, float* dL_dcolor, float* dL_dallmap, float* dL_dbkgd,
+                                float* surf_depth_scratch, void* stream);
+
 SR_API int sr_abi_version(void);
 SR_API const char* sr_last_error(void);
 /* number of kernel launches issued by this library since load (bench.py's `gpu_launches`) */

@@ -145,11 +145,14 @@ def mask_balance_wt(mask, vis2d):
 
 
 def stage3_losses(color, allmap, wvt, tanx, tany, depth_ratio, target_rgb, vis2d, mask_gt, mask_wt,
-                  w_rgb=1.0, w_mask=1.0, lambda_normal=0.05, lambda_dist=0.01):
+                  w_rgb=1.0, w_mask=1.0, lambda_normal=0.05, lambda_dist=0.01, bkgd=None):
     """The image-space losses of one Stage-3 frame (float64).  Returns (total, dict of the four terms).
-    color (3,H,W) rendered image, target_rgb (3,H,W), vis2d / mask_gt / mask_wt (H,W)."""
+    color (3,H,W) rendered image, target_rgb (3,H,W), vis2d / mask_gt / mask_wt (H,W); bkgd (3,) = the learnable
+    background composited under the render first (lab4d/nnutils/deformable_gaussian.py:188-190)."""
     c = np.asarray(color, np.float64)
     fw = post_forward(allmap, wvt, tanx, tany, depth_ratio)
+    if bkgd is not None:
+        c = c + (1.0 - fw["acc"]) * np.asarray(bkgd, np.float64)[:, None, None]
     vis = (np.asarray(vis2d) > 0)
     l1 = (np.abs(c - np.asarray(target_rgb, np.float64)) * vis[None]).mean()          # zeros where vis2d == 0, mean over all
     lmask = (((fw["acc"][0] - np.asarray(mask_gt, np.float64)) ** 2) * np.asarray(mask_wt, np.float64)).mean()
@@ -160,18 +163,25 @@ def stage3_losses(color, allmap, wvt, tanx, tany, depth_ratio, target_rgb, vis2d
 
 
 def stage3_losses_backward(color, allmap, wvt, tanx, tany, depth_ratio, target_rgb, vis2d, mask_gt, mask_wt,
-                           w_rgb=1.0, w_mask=1.0, lambda_normal=0.05, lambda_dist=0.01):
-    """d total / d color (3,H,W) and d total / d allmap (8,H,W), float64."""
+                           w_rgb=1.0, w_mask=1.0, lambda_normal=0.05, lambda_dist=0.01, bkgd=None):
+    """d total / d color (3,H,W), d total / d allmap (8,H,W) and (if bkgd is given) d total / d bkgd (3,), float64."""
     c = np.asarray(color, np.float64)
     _, H, W = c.shape
     N = H * W
     fw = post_forward(allmap, wvt, tanx, tany, depth_ratio)
     vis = (np.asarray(vis2d) > 0)
+    bk = None if bkgd is None else np.asarray(bkgd, np.float64)
+    if bk is not None:
+        c = c + (1.0 - fw["acc"]) * bk[:, None, None]
     g_color = w_rgb * np.sign(c - np.asarray(target_rgb, np.float64)) * vis[None] / (3.0 * N)
+    g_acc_bk = 0.0 if bk is None else -(g_color * bk[:, None, None]).sum(0)
     grads = {
-        "acc": (w_mask * 2.0 * (fw["acc"][0] - np.asarray(mask_gt, np.float64)) * np.asarray(mask_wt, np.float64) / N)[None],
+        "acc": (w_mask * 2.0 * (fw["acc"][0] - np.asarray(mask_gt, np.float64)) * np.asarray(mask_wt, np.float64) / N + g_acc_bk)[None],
         "rend_normal": -lambda_normal * fw["surf_normal"] / N,
         "surf_normal": -lambda_normal * fw["rend_normal"] / N,
         "rend_dist": np.full((1, H, W), lambda_dist / N),
     }
-    return g_color, post_backward(allmap, wvt, tanx, tany, depth_ratio, grads)
+    g_allmap = post_backward(allmap, wvt, tanx, tany, depth_ratio, grads)
+    if bk is None:
+        return g_color, g_allmap
+    return g_color, g_allmap, (g_color * (1.0 - fw["acc"])).sum((1, 2))

@@ -18,7 +18,7 @@ SR_STATUS_PREFILTER = 4
 SYMBOLS = (
     "sr_geom_bytes", "sr_image_bytes", "sr_binning_bytes", "sr_forward", "sr_backward",
     "sr_mark_visible", "sr_debug_view", "sr_abi_version", "sr_last_error", "sr_launch_count",
-    "sr_set_profiling", "sr_get_profile", "sr_post_forward", "sr_post_backward", "sr_forward_batch", "sr_backward_batch",
+    "sr_set_profiling", "sr_get_profile", "sr_post_forward", "sr_post_backward", "sr_forward_batch", "sr_backward_batch", "sr_render_loss_batch",
 )
 
 
@@ -93,6 +93,8 @@ def load():
     lib.sr_post_forward.argtypes = [i32, i32, C.c_float, C.c_float, C.c_float] + [vp] * 10
     lib.sr_post_backward.restype = C.c_int
     lib.sr_post_backward.argtypes = [i32, i32, C.c_float, C.c_float, C.c_float] + [vp] * 12
+    lib.sr_render_loss_batch.restype = C.c_int
+    lib.sr_render_loss_batch.argtypes = [i32, i32, i32, C.c_float, C.c_float, C.c_float] + [vp] * 8 + [C.c_float] * 4 + [vp] * 6
     lib.sr_set_profiling.restype = None
     lib.sr_set_profiling.argtypes = [C.c_int]
     lib.sr_get_profile.restype = C.c_char_p

@@ -33,6 +33,20 @@ def _tan_half(fov) -> float:
     return math.tan(float(fov) * 0.5)
 
 
+def _cam_tans(cam):
+    """(tan(FoVx/2), tan(FoVy/2)) of a camera, computed ONCE per camera object: the reference's KCamera keeps FoVx/FoVy as
+    tensors (gs/scene/cameras.py:86-87), possibly on the GPU, and reading them costs a host sync per call -- which
+    also makes the call uncapturable in a CUDA graph.  The pair is cached on the object (cameras are immutable in Vidu4D)."""
+    t = getattr(cam, "_sr_tans", None)
+    if t is None:
+        t = (_tan_half(cam.FoVx), _tan_half(cam.FoVy))
+        try:
+            object.__setattr__(cam, "_sr_tans", t)
+        except Exception:
+            pass
+    return t
+
+
 # ---------------------------------------------------------------------------------------------
 # cameras (gs/scene/cameras.py, gs/utils/graphics_utils.py) -- input contract only
 # ---------------------------------------------------------------------------------------------
@@ -108,7 +122,7 @@ def _rays(view, device):
     the adjugate formula, so the reference's per-call torch.tensor(...).cuda(), .inverse() and math.tan(cuda
     tensor) syncs are gone."""
     W, H = int(view.image_width), int(view.image_height)
-    tx, ty = _tan_half(view.FoVx), _tan_half(view.FoVy)
+    tx, ty = _cam_tans(view)
     key = (W, H, tx, ty, str(device))
     dirs = _dir_cache.get(key)
     if dirs is None:
@@ -159,8 +173,7 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=
     except Exception:
         pass
 
-    tanfovx = _tan_half(viewpoint_camera.FoVx)
-    tanfovy = _tan_half(viewpoint_camera.FoVy)
+    tanfovx, tanfovy = _cam_tans(viewpoint_camera)
     raster_settings = GaussianRasterizationSettings(
         image_height=int(viewpoint_camera.image_height),
         image_width=int(viewpoint_camera.image_width),
@@ -285,8 +298,7 @@ def render_fused(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_mod
         screenspace_points.retain_grad()
     except Exception:
         pass
-    tanfovx = _tan_half(viewpoint_camera.FoVx)
-    tanfovy = _tan_half(viewpoint_camera.FoVy)
+    tanfovx, tanfovy = _cam_tans(viewpoint_camera)
     raster_settings = GaussianRasterizationSettings(
         image_height=int(viewpoint_camera.image_height), image_width=int(viewpoint_camera.image_width),
         tanfovx=tanfovx, tanfovy=tanfovy, bg=bg_color, scale_modifier=scaling_modifier,
@@ -320,3 +332,114 @@ class PipelineParams:
     compute_cov3D_python: bool = False
     depth_ratio: float = 0.0
     debug: bool = False
+
+
+# ---------------------------------------------------------------------------------------------
+# Batched Stage-3 inner loop: M frames -> rasterize -> post-process -> image losses, one launch set each way
+# (SURVEY.md section 8(f) row N1).  Replaces the Python frame loop of lab4d/nnutils/deformable_gaussian.py:1175-1188 and
+# the ~40 torch kernels per frame of lab4d/engine/model.py:674-692,817-842.
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class BatchCameras:
+    """M cameras sharing resolution and field of view (Stage 3: gs/scene/cameras.py:72-162 builds them per frame)."""
+    image_width: int
+    image_height: int
+    FoVx: float
+    FoVy: float
+    world_view_transform: torch.Tensor   # (M,4,4), each W2C transposed
+    full_proj_transform: torch.Tensor    # (M,4,4)
+    camera_center: torch.Tensor          # (M,3)
+
+    def __len__(self):
+        return int(self.world_view_transform.shape[0])
+
+
+def stack_cameras(cams) -> BatchCameras:
+    c0 = cams[0]
+    return BatchCameras(int(c0.image_width), int(c0.image_height), c0.FoVx, c0.FoVy,
+                        torch.stack([c.world_view_transform for c in cams]).contiguous(),
+                        torch.stack([c.full_proj_transform for c in cams]).contiguous(),
+                        torch.stack([c.camera_center for c in cams]).contiguous())
+
+
+class _RasterLossBatch(torch.autograd.Function):
+    """rasterize M frames -> fused post-processing + losses.  The loss kernel already produced dL/dcolor and dL/dallmap,
+    so backward() is just the rasterizer backward with the upstream scalar as `grad_scale`."""
+
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, opacities, scales, rotations, bkgd, cfg):
+        from . import _capi
+        from .rasterizer import _C
+        lib = _capi.load()
+        cams, bg, sh_degree, target, vis, mask, mask_wt, depth_ratio, w_rgb, w_mask, lam_n, lam_d, tanx, tany = cfg
+        M, H, W = len(cams), cams.image_height, cams.image_width
+        dev = means3D.device
+        e = torch.empty((0,), dtype=torch.float32, device=dev)
+        nr, color, allmap, radii, gb, bb, ib = _C.rasterize_gaussians_batch(
+            bg, means3D, e, opacities, scales, rotations, 1.0, cams.world_view_transform, cams.full_proj_transform, tanx, tany,
+            H, W, sh, sh_degree, cams.camera_center)
+        terms = torch.empty((M, 4), dtype=torch.float32, device=dev)
+        dLc = torch.empty_like(color)
+        dLa = torch.empty_like(allmap)
+        dLb = torch.empty((M, 3), dtype=torch.float32, device=dev) if bkgd is not None else None
+        scratch = torch.empty((M, H, W), dtype=torch.float32, device=dev)
+        ptr = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+        f32 = lambda t: None if t is None else t.to(dtype=torch.float32).contiguous()  # noqa: E731
+        target, vis, mask, mask_wt = f32(target), f32(vis), f32(mask), f32(mask_wt)
+        bk = f32(bkgd.detach()) if bkgd is not None else None
+        with torch.cuda.device(dev):
+            rc = lib.sr_render_loss_batch(M, W, H, tanx, tany, float(depth_ratio), color.data_ptr(), allmap.data_ptr(),
+                                          cams.world_view_transform.data_ptr(), target.data_ptr(), ptr(vis), ptr(mask), ptr(mask_wt),
+                                          ptr(bk), float(w_rgb), float(w_mask), float(lam_n), float(lam_d), terms.data_ptr(),
+                                          dLc.data_ptr(), dLa.data_ptr(), ptr(dLb), scratch.data_ptr(),
+                                          torch.cuda.current_stream(dev).cuda_stream)
+        _capi.check(rc, "sr_render_loss_batch")
+        total = terms.sum()
+        ctx.cfg = (cams, bg, sh_degree, tanx, tany)
+        ctx.has_bkgd = bkgd is not None
+        ctx.save_for_backward(means3D, scales, rotations, radii, sh, opacities, gb, bb, ib, dLc, dLa,
+                              dLb if dLb is not None else e)
+        ctx.mark_non_differentiable(terms, color, allmap, radii)
+        return total, terms, color, allmap, radii
+
+    @staticmethod
+    def backward(ctx, g_total, g_terms, g_color, g_allmap, g_radii):
+        from .rasterizer import _C, _reduce_like
+        cams, bg, sh_degree, tanx, tany = ctx.cfg
+        means3D, scales, rotations, radii, sh, opacities, gb, bb, ib, dLc, dLa, dLb = ctx.saved_tensors
+        e = torch.empty((0,), dtype=torch.float32, device=means3D.device)
+        g2d, gcol, gop, g3d, gtm, gsh, gsc, grot = _C.rasterize_gaussians_backward_batch(
+            bg, means3D, radii, e, scales, rotations, 1.0, cams.world_view_transform, cams.full_proj_transform, tanx, tany,
+            dLc, dLa, sh, sh_degree, cams.camera_center, gb, bb, ib, grad_scale=g_total)
+        g_bk = (dLb.sum(0) * g_total) if ctx.has_bkgd else None
+        return (_reduce_like(g3d, means3D), g2d, _reduce_like(gsh, sh), _reduce_like(gop, opacities),
+                _reduce_like(gsc, scales), _reduce_like(grot, rotations), g_bk, None)
+
+
+def render_loss_batch(cameras, pc, pipe, bg_color, target_rgb, vis2d=None, mask_gt=None, mask_wt=None, learnable_bkgd=None,
+                      w_rgb=1.0, w_mask=0.0, lambda_normal=0.0, lambda_dist=0.0, means3D=None, rotations=None):
+    """The Stage-3 inner loop for M frames in one call: rasterize every frame (batched launch set), post-process and
+    evaluate the image losses in one fused kernel, and hand autograd a single scalar.
+
+    cameras: BatchCameras (or a list of cameras, stacked here).  pc: as in render().  means3D (M,P,3) / rotations (M,P,4):
+    optional per-frame overrides -- the bob-warped surfels of each frame (DeformableGaussian._override_xyz/_rotation,
+    lab4d/nnutils/deformable_gaussian.py:163-176); default = pc.get_xyz / pc.get_rotation shared by all frames.
+    target_rgb (M,3,H,W); vis2d / mask_gt / mask_wt (M,H,W) or None; learnable_bkgd (3,) or None.
+
+    Returns {"loss": scalar (sum over frames and terms, differentiable), "terms": (M,4) weighted rgb/mask/normal/dist
+    (detached), "render": (M,3,H,W), "allmap": (M,8,H,W), "radii": (M,P), "visibility_filter": (M,P),
+    "viewspace_points": (M,P,3) whose .grad receives the densification proxy}."""
+    if not isinstance(cameras, BatchCameras):
+        cameras = stack_cameras(cameras)
+    M = len(cameras)
+    xyz = pc.get_xyz if means3D is None else means3D
+    rot = pc.get_rotation if rotations is None else rotations
+    P = int(xyz.shape[-2])
+    screenspace_points = torch.zeros((M, P, 3), dtype=xyz.dtype, requires_grad=True, device=xyz.device)
+    tanx, tany = _cam_tans(cameras)
+    cfg = (cameras, bg_color, pc.active_sh_degree, target_rgb, vis2d, mask_gt, mask_wt, float(pipe.depth_ratio),
+           w_rgb, w_mask, lambda_normal, lambda_dist, tanx, tany)
+    total, terms, color, allmap, radii = _RasterLossBatch.apply(xyz, screenspace_points, pc.get_features, pc.get_opacity,
+                                                                pc.get_scaling, rot, learnable_bkgd, cfg)
+    return {"loss": total, "terms": terms, "render": color, "allmap": allmap, "radii": radii,
+            "visibility_filter": radii > 0, "viewspace_points": screenspace_points}

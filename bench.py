@@ -8,6 +8,8 @@
 A STEP = one pass of the hot path over one batch: every rank rasterizes `--frames-per-step` frames (forward +
 backward, each frame a different camera), accumulates the surfel gradients, and -- for N > 1 -- joins ONE NCCL
 all-reduce of the flat gradient buffer (frames are the shard axis; weak scaling: per-GPU work is fixed).
+Ours: the F frames of a step are ONE batched launch set (sr_forward_batch / sr_backward_batch: every kernel has a frame
+dimension), captured in a CUDA graph; `--mode streams` keeps round 1's harness (F single-frame calls over S streams).
 
 One JSON line (rank 0):
   value       frames/s over all ranks, inputs resident in HBM, C-ABI calls, device-event timed (max over ranks)
@@ -56,7 +58,10 @@ def parse():
     ap.add_argument("--res", type=int, default=512)
     ap.add_argument("--frames-per-step", type=int, default=8)
     ap.add_argument("--opacity", default="trained", choices=["trained", "init"])
-    ap.add_argument("--cpu-frames", type=int, default=2, help="frames of the cpu_baseline sample (0 = skip)")
+    ap.add_argument("--cpu-frames", type=int, default=8, help="frames of the cpu_baseline sample after one warm-up frame (0 = skip)")
+    ap.add_argument("--mode", default="batch", choices=["batch", "streams"], help="ours: one batched launch set per step, or F single-frame calls over --streams CUDA streams")
+    ap.add_argument("--no-value-graph", action="store_true", help="keep the value-arm step eager (no CUDA-graph capture)")
+    ap.add_argument("--no-variants", action="store_true", help="skip the 1- and 2-frame-per-call variants of the value arm")
     ap.add_argument("--no-ref-cuda", action="store_true", help="skip timing the reference extension in the ours arm")
     ap.add_argument("--ref-device", default="cuda", choices=["cuda", "cpu"])
     ap.add_argument("--no-graph", action="store_true", help="keep the e2e step eager (no CUDA-graph capture)")
@@ -213,15 +218,16 @@ def main():
                                                       vms[v], pms[v], TAN, TAN, dLc, dLo, t_in["shs"], 3, cps[v], o[4],
                                                       o[0], o[5], o[6], False)
 
-    # Frames of a step are independent: alternate them over `--streams` CUDA streams so that one frame's tail
-    # (a few long composite warps, ncu: SMs 14-20 % idle) overlaps other frames' heads.  Each stream sums the
-    # gradients of its frames into its own row of one [streams, floats] buffer (first frame of the step assigns, the
-    # rest add); one reduction over the rows per step gives the step's flat gradient -- the buffer the all-reduce uses.
-    NS = max(1, args.streams) if args.impl == "ours" else 1
-    side = [torch.cuda.Stream(device=device) for _ in range(max(NS, 2))]   # also used by the e2e step
+    # ---- ours, default: the F frames of a step are ONE batched launch set; the step (camera gather -> forward -> backward ->
+    # sum over frames into the flat gradient) is captured in a CUDA graph, then one NCCL all-reduce and the step's only
+    # host<->device synchronisation (check_overflow).  `--mode streams` keeps round 1's harness: F single-frame calls
+    # alternating over `--streams` CUDA streams, per-stream gradient rows reduced once per step.
+    BATCH = args.impl == "ours" and args.mode == "batch"
+    NS = 1 if (args.impl != "ours" or BATCH) else max(1, args.streams)
+    side = [torch.cuda.Stream(device=device) for _ in range(max(NS, 2))]
     nflt = acc_flat_bytes // 4
     stack = torch.zeros((NS, nflt), device=device)
-    flat_acc = torch.zeros((nflt,), device=device) if NS > 1 else stack[0]
+    flat_acc = torch.zeros((nflt,), device=device) if (NS > 1 or BATCH) else stack[0]
 
     def views(row):
         out, o_ = [], 0
@@ -229,10 +235,45 @@ def main():
             out.append(row[o_:o_ + a.numel()].view(a.shape)); o_ += a.numel()
         return out
     accs = [views(stack[k]) for k in range(NS)]
+    flat_views = views(flat_acc)
+    flat_outs = dict(zip(("dL_dmeans3D", "dL_dsh", "dL_dopacity", "dL_dscales", "dL_drotations"), flat_views))
     GIDX = (3, 5, 2, 6, 7)      # gr = (dmeans2D, dcolors, dopacity, dmeans3D, dtransMat, dsh, dscales, drots)
+    step_ctr = torch.zeros((), dtype=torch.int64, device=device)      # lives on the device: the captured step advances it
+    ar = torch.arange(F, device=device)
+    dLc_b = dLc.expand(F, -1, -1, -1).contiguous() if BATCH else None
+    dLo_b = dLo.expand(F, -1, -1, -1).contiguous() if BATCH else None
+    value_graph = [None]
+    R_last_box = [0]
+
+    def batch_body(fpc=None):
+        """One batched forward+backward of `fpc` frames (default F) + the sum over frames into the flat gradient."""
+        n = F if fpc is None else fpc
+        idx = (step_ctr * (world * F) + rank * F + ar[:n]) % NVIEWS
+        step_ctr.add_(1)
+        vm_b, pm_b, cp_b = vms.index_select(0, idx), pms.index_select(0, idx), cps.index_select(0, idx)
+        o = C.rasterize_gaussians_batch(bg, t_in["means3D"], e, t_in["opac"], t_in["scales"], t_in["rots"], 1.0, vm_b, pm_b,
+                                        TAN, TAN, RES, RES, t_in["shs"], 3, cp_b)
+        # gradients of the (shared) surfel parameters are summed over the frames inside the per-surfel kernel and land
+        # directly in the flat buffer the all-reduce runs over
+        gr = C.rasterize_gaussians_backward_batch(bg, t_in["means3D"], o[3], e, t_in["scales"], t_in["rots"], 1.0, vm_b, pm_b,
+                                                  TAN, TAN, dLc_b[:n], dLo_b[:n], t_in["shs"], 3, cp_b, o[4], o[5], o[6],
+                                                  sum_shared=True, want_transmat=False, outs=flat_outs if n == F else None)
+        if n != F:      # the 1- and 2-frames-per-call variants: several calls per step accumulate into the flat buffer
+            for a_, gi in zip(flat_views, GIDX):
+                a_.add_(gr[gi].reshape(a_.shape))
+        return o
 
     def step_dev(step):
         R_last = 0
+        if BATCH:
+            if value_graph[0] is not None:
+                value_graph[0].replay()
+            else:
+                batch_body()
+            if world > 1:
+                torch.distributed.all_reduce(flat_acc)
+            RZ.check_overflow(keep=value_graph[0] is not None)     # the step's only host<->device synchronisation
+            return R_last
         main = torch.cuda.current_stream()
         if NS > 1:
             for st_ in side:
@@ -261,6 +302,43 @@ def main():
             RZ.check_overflow()     # the step's only host<->device synchronisation
         return R_last
 
+    def capture(body_fn, what):
+        """Warm up eagerly (allocator pools, capacity hints), then capture body_fn into a CUDA graph; None on failure."""
+        try:
+            RZ.set_sync_mode(True); body_fn(); RZ.set_sync_mode(False)      # learn the instance capacity
+            for _ in range(2):
+                body_fn()
+            RZ.check_overflow()
+            RZ.reserve_host_slots(8)
+            warm = torch.cuda.Stream(device=device)
+            warm.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(warm):
+                body_fn(); RZ.check_overflow()
+            torch.cuda.current_stream().wait_stream(warm)
+            torch.cuda.synchronize()
+            RZ.reserve_host_slots(8)
+            gph = torch.cuda.CUDAGraph()
+            lc0 = _capi.launch_count()
+            with torch.cuda.graph(gph):
+                body_fn()
+            gph.launches = _capi.launch_count() - lc0      # kernels of OUR library one replay launches
+            gph.watch = list(RZ._pending)      # the pinned status words this graph rewrites on every replay
+            return gph
+        except Exception as ex:   # pragma: no cover
+            sys.stderr.write(f"[bench] CUDA-graph capture of {what} failed: {ex!r}\n")
+            RZ._pending.clear()
+            torch.cuda.synchronize()
+            return None
+
+    def arm(gph):
+        """Make check_overflow(keep=True) watch the status words of the graph that is about to be replayed."""
+        RZ._pending[:] = gph.watch if gph is not None else []
+
+    value_mode = "eager"
+    if BATCH and not args.no_value_graph:
+        value_graph[0] = capture(batch_body, "the value-arm step")
+        value_mode = "cuda_graph(batched forward+backward+frame-sum)" if value_graph[0] is not None else "eager (capture failed)"
+
     def timed(step_fn, nsteps, nwarm):
         for s in range(nwarm):
             step_fn(s)
@@ -282,11 +360,36 @@ def main():
     if rank == 0:
         sampler.start()
     launches0 = _capi.launch_count() if args.impl == "ours" else 0
+    if BATCH:
+        arm(value_graph[0])
     total_ms, per_ms, wall_ms = timed(step_dev, K, Wm)
     launches = (_capi.launch_count() - launches0) if args.impl == "ours" else None
+    if BATCH and value_graph[0] is not None:
+        launches = value_graph[0].launches * K          # graph replays do not pass through the library's host-side counter
     total_ms = max_over_ranks(total_ms, world, device)
     frames = K * F * world
     value = frames / (total_ms * 1e-3)
+
+    # the same F frames per step with 1 and 2 frames per call (Stage 3 renders M = 2 frames per step,
+    # lab4d/engine/trainer.py:453-468): what the path delivers when the caller cannot batch 8 frames
+    variants = None
+    if BATCH and world == 1 and not args.no_variants:
+        variants = {}
+        for n in (1, 2):
+            gph = capture(lambda: batch_body(n), f"the {n}-frame variant")
+
+            def vstep(step, gph=gph, n=n):
+                for _ in range(F // n):
+                    if gph is not None:
+                        gph.replay()
+                    else:
+                        batch_body(n)
+                RZ.check_overflow(keep=gph is not None)
+            arm(gph)
+            vt, _, _ = timed(vstep, max(3, K // 2), 3)
+            variants[f"frames_per_call_{n}"] = round(max(3, K // 2) * F / (vt * 1e-3), 2)
+            del gph
+        arm(value_graph[0])
 
     # R (instances) of a representative frame, for the algorithmic-byte figures
     if args.impl == "ours":
@@ -300,6 +403,8 @@ def main():
         _dec = _dbg.decode(o_probe[4], o_probe[5], o_probe[6], P, RES, RES, R_inst)
         _rg = _dec["ranges"].to(torch.int64)
         pair_upper = int(((_rg[:, 1] - _rg[:, 0]) * 256).sum().item())
+        pairs_contrib = _dbg.contributing_pairs(_dec)          # (pixel, instance) pairs that passed every test
+        V_vis = int((o_probe[3] > 0).sum().item())             # visible surfels of the probe frame
         del _dec, _rg
         RZ.set_sync_mode(False)
     else:
@@ -331,7 +436,7 @@ def main():
     e2e_streams = [1]
     tots = [torch.zeros((), device=device) for _ in range(8)]
 
-    def body():
+    def body_frames():
         """H2D of this step's inputs -> render x F -> loss -> backward (everything a CUDA graph can hold).  Frames
         alternate over e2e_streams[0] streams; autograd runs each frame's backward on its forward stream and
         serialises the accumulation into the (flat) .grad buffers itself."""
@@ -361,6 +466,28 @@ def main():
                 main.wait_stream(side[k])
         tot.copy_(torch.stack(tots).sum())
 
+    if BATCH:
+        from vidu4d_b200.renderer import BatchCameras, render_loss_batch
+
+        def body_batch():
+            """H2D of this step's inputs -> ONE batched rasterize + fused post-processing + losses -> ONE batched backward."""
+            main = torch.cuda.current_stream()
+            cam.copy_(cam_h, non_blocking=True); cp.copy_(cps_hh, non_blocking=True)
+            side[0].wait_stream(main)
+            with torch.cuda.stream(side[0]):           # the step's target images upload beside the rasterizer forward
+                tg.copy_(targets_h, non_blocking=True)
+            fg.zero_()
+            bc = BatchCameras(RES, RES, fov, fov, cam[:, 0], cam[:, 1], cp)
+            out = render_loss_batch(bc, cloud, pipe, bg, tg, w_rgb=1.0, lambda_normal=0.05, lambda_dist=0.01,
+                                    target_stream=side[0])
+            out["loss"].backward()
+            tot.copy_(out["loss"].detach())
+
+    body_sel = [body_batch if BATCH else body_frames]
+
+    def body():
+        body_sel[0]()
+
     freeze = [False]
 
     def tail():
@@ -386,12 +513,13 @@ def main():
     if args.impl == "ours" and not args.no_graph:
         # The sync-free forward makes the whole step capturable: one cudaGraphLaunch replaces ~150 small launches.
         # (The reference cannot be captured: its forward blocks on a D2H copy, rasterizer_impl.cu:282.)
-        for ns_try in (sorted({min(NS, 8, F), min(NS, 4), min(NS, 2), 1}, reverse=True) if NS > 1 else [1]):
+        for ns_try in (sorted({min(NS, 8, F), min(NS, 4), min(NS, 2), 1}, reverse=True) if (NS > 1 and not BATCH) else [1]):
             try:
                 e2e_streams[0] = ns_try
                 for s_ in range(2):
                     step_e2e(s_)                               # eager warm-up: allocator pools, caches, capacity hints
                 RZ.check_overflow()
+                RZ._pending.clear()
                 RZ.reserve_host_slots(F + 4)
                 gph = torch.cuda.CUDAGraph()
                 warm = torch.cuda.Stream(device=device)
@@ -404,7 +532,9 @@ def main():
                 with torch.cuda.graph(gph):
                     body()
                 graph = gph
-                e2e_mode = f"cuda_graph(H2D+render+loss+backward, {ns_try} stream(s)) + eager all-reduce/Adam/readback"
+                graph.watch = list(RZ._pending)
+                e2e_mode = (f"cuda_graph(H2D + batched render_loss_batch + backward, 1 stream) + eager all-reduce/Adam/readback" if BATCH else
+                            f"cuda_graph(H2D+render+loss+backward, {ns_try} stream(s)) + eager all-reduce/Adam/readback")
                 break
             except Exception as ex:   # pragma: no cover
                 sys.stderr.write(f"[bench] CUDA-graph capture of the e2e step ({ns_try} streams) failed: {ex!r}\n")
@@ -426,6 +556,10 @@ def main():
         g_mode = fg.flat.clone()
         keep_graph, keep_ns = graph, e2e_streams[0]
         graph, e2e_streams[0] = None, 1
+        RZ._pending.clear()
+        # the eager leg is round 1's per-frame path: render_fused() + the torch loss expressions + autograd -- an
+        # independent evaluation of what the batched fused-loss step computes
+        body_sel[0] = body_frames
         l_eager = step_e2e(1000)
         torch.cuda.synchronize()
         g_eager = fg.flat.clone()
@@ -433,11 +567,14 @@ def main():
         torch.cuda.synchronize()
         g_eager2 = fg.flat.clone()
         graph, e2e_streams[0] = keep_graph, keep_ns
+        body_sel[0] = body_batch if BATCH else body_frames
+        RZ._pending[:] = graph.watch if graph is not None else []
         freeze[0] = False
         nrm = float(g_eager.double().norm() + 1e-30)
         e2e_check = {"loss_mode": l_mode, "loss_eager": l_eager,
                      "grad_rel_l2_diff": float((g_mode - g_eager).double().norm()) / nrm,
-                     "eager_self_rel_l2_diff": float((g_eager2 - g_eager).double().norm()) / nrm}
+                     "eager_self_rel_l2_diff": float((g_eager2 - g_eager).double().norm()) / nrm,
+                     "eager_path": "per-frame render_fused() + torch losses + autograd"}
 
     e2e_total, _, _ = timed(step_e2e, K, Wm)
     e2e_total = max_over_ranks(e2e_total, world, device)
@@ -455,46 +592,65 @@ def main():
     peak_src = "MEASURED_PEAKS.json (measured)" if peaks else "B200_PROFILING.md fallback 6650 GB/s"
     N = RES * RES
     if args.impl == "ours" and rank == 0:
-        # single stream, nothing else in flight: the per-kernel CUDA events must not span another stream's work
-        for f in range(2):
-            frame_dev(f % NVIEWS)
+        # The same step as the timed region, eager, with the library's per-kernel CUDA events switched on
+        # (sr_set_profiling: events on the launching stream around every kernel; nothing else is in flight).
+        RZ._pending.clear()
+        prof_step = (lambda: batch_body()) if BATCH else (lambda: [frame_dev(f % NVIEWS) for f in range(F)])
+        prof_step()
         torch.cuda.synchronize()
         _capi.get_profile()
         _capi.set_profiling(True)
-        nprof = 6
-        for f in range(nprof):
-            frame_dev(f % NVIEWS)
+        nprof = 3
+        for _ in range(nprof):
+            prof_step()
         prof = _capi.get_profile()
         _capi.set_profiling(False)
         RZ.check_overflow()
-        Vv = P
-        alg = {   # algorithmic bytes per launch (DESIGN.md "algorithmic bytes")
-            "preprocess_fwd": P * (40 + 12 * 16) + Vv * 93,
-            "scan_block_sums": (P // 256) * 8, "emit_keys": P * 20 + R_inst * 12,
-            "sort_histogram": R_inst * 8, "sort_plan": 6 * 256 * 8, "onesweep_passes": R_inst * 24 * 6,
-            "ranges_gather": R_inst * (12 + 80 + 80), "composite_fwd": R_inst * 112 + N * 64,
-            "composite_bwd": R_inst * 112 + N * 64 + Vv * 72, "surfel_bwd": Vv * (343 + 240),
+        Fl = F if BATCH else 1                       # frames one launch processes
+        Vv = V_vis
+        # ALGORITHMIC bytes per frame of each kernel (split per kernel in DESIGN.md section 3);
+        # implementation-only traffic (contribution masks, instance-record stream written by the gather) is listed apart
+        alg = {
+            "preprocess_fwd": P * (40 + 12 * 16) + Vv * 87, "scan_block_sums": (P // 256) * 8,
+            "emit_keys": P * 20 + R_inst * 12, "sort_histogram": R_inst * 8, "sort_plan": 6 * 256 * 8,
+            "onesweep_passes": R_inst * 24 * 6, "ranges_gather": R_inst * 8 + 8 * (RES // 16) ** 2,
+            "composite_fwd": R_inst * 76 + N * 64, "composite_bwd": R_inst * 76 + N * 64 + Vv * 72,
+            "surfel_bwd": Vv * (343 + 240), "tile_order": 12 * (RES // 16) ** 2,
         }
+        impl = {"ranges_gather": R_inst * (12 + 80 + 80), "composite_fwd": R_inst * (80 + 32) + N * 64,
+                "composite_bwd": R_inst * (80 + 32) + N * 64 + Vv * 80}
         kernels = {}
         for k, v in prof.items():
-            ms = v["ms"] / max(v["count"], 1)
-            kernels[k] = {"ms": round(ms, 5), "alg_MB": round(alg.get(k, 0) / 1e6, 2),
-                          "GBps": round(alg.get(k, 0) / 1e9 / (ms * 1e-3), 1) if ms > 0 else None}
-        dom = max(kernels, key=lambda k: kernels[k]["ms"])
+            ms = v["ms"] / max(v["count"], 1)                       # per launch
+            ab = alg.get(k, 0) * Fl
+            kernels[k] = {"ms_per_launch": round(ms, 5), "ms_per_frame": round(ms / Fl, 5), "frames_per_launch": Fl,
+                          "alg_MB_per_launch": round(ab / 1e6, 2), "GBps": round(ab / 1e9 / (ms * 1e-3), 1) if ms > 0 else None}
+            if k in impl:
+                kernels[k]["impl_MB_per_launch"] = round(impl[k] * Fl / 1e6, 2)
+        dom = max(kernels, key=lambda k: kernels[k]["ms_per_launch"])
         ach = kernels[dom]["GBps"]
-        traffic = None
-        try:   # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[dom]["dram_bytes_per_launch"]
+        ncu = {}
+        try:   # counters of that kernel from the committed `ncu --set full` capture (per launch of ONE frame)
+            ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(dom, {})
         except Exception:
             pass
+        traffic = ncu.get("dram_bytes_per_launch")
+        frame_alg = 1002 * P + 324 * R_inst + 128 * N
         roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                     "frac": round(ach / hbm_peak, 5), "traffic": traffic, "peak_source": peak_src,
-                    "note": "the composite kernels are FP32-issue/shared-memory bound by construction (SURVEY 8d); "
-                            "algorithmic HBM bytes are small, see profiles/ for ncu pipe utilisation",
+                    "alg_bytes_per_launch": alg.get(dom, 0) * Fl, "impl_bytes_per_launch": impl.get(dom, alg.get(dom, 0)) * Fl,
+                    "launch_ms": kernels[dom]["ms_per_launch"], "frames_per_launch": Fl,
+                    "traffic_note": "dram bytes of ONE frame's launch from profiles/ncu_traffic.json (ncu --set full)",
+                    "l2_red_sectors": ncu.get("l2_red_sectors"), "lanes_active": ncu.get("lanes_active"),
+                    "contributing_pairs": pairs_contrib, "visible_surfels": Vv,
+                    "note": "the composite kernels are FP32-issue / latency bound by construction (SURVEY 8d): each instance record "
+                            "is read once per tile but evaluated against ~10 pixels; algorithmic HBM bytes are small. "
+                            "pairs/s is the explanatory figure, profiles/ holds the ncu pipe utilisation",
+                    "contributing_pairs_per_s": round(pairs_contrib * (K * F * world) / (total_ms * 1e-3), 0),
                     "pair_evals_upper_per_frame": pair_upper,
-                    "pair_evals_upper_per_s": round(pair_upper * (K * F * world) / (total_ms * 1e-3), 0),
-                    "frame_alg_MB": round((1002 * P + 324 * R_inst + 128 * N) / 1e6, 1),
-                    "frame_GBps": round((1002 * P + 324 * R_inst + 128 * N) / 1e9 / (total_ms * 1e-3 / (K * F)), 1)}
+                    "frame_alg_MB": round(frame_alg / 1e6, 1),
+                    "frame_GBps": round(frame_alg / 1e9 / (total_ms * 1e-3 / (K * F)), 1),
+                    "frame_frac": round(frame_alg / 1e9 / (total_ms * 1e-3 / (K * F)) / hbm_peak, 4)}
 
     # ---------------- reference CUDA extension in the same run (ours arm, rank 0, N=1) ----------------
     reference_cuda = None
@@ -532,13 +688,14 @@ def main():
                                    f"{F} frames/step/GPU on orbiting cameras, colour+depth+normal+distortion fwd+bwd",
                        "surfels": P, "resolution": RES, "frames_per_step_per_gpu": F, "instances_per_frame": R_inst,
                        "parallelism": f"frames sharded over {world} GPU(s), 1 NCCL all-reduce of {acc_flat_bytes >> 20} MiB/step" if world > 1 else "1 GPU",
-                       "streams": NS,
+                       "streams": NS, "mode": (args.mode if args.impl == "ours" else "reference: single-frame calls, legacy default stream"),
+                       "value_step": value_mode,
                        "l2": f"explicit flush (256 MiB write) between timed steps; per-step working set also exceeds the {L2_MB} MB L2"},
             "e2e": {"value": round(e2e_value, 2), "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
-                    "mode": e2e_mode, "check_vs_eager": e2e_check, "api": "render_fused" if render is render_fused else "render",
+                    "mode": e2e_mode, "check_vs_eager": e2e_check, "api": "render_loss_batch" if BATCH else ("render_fused" if render is render_fused else "render"),
                     "what": "render() -> L1+normal+distortion loss -> backward -> (all-reduce) -> fused Adam; per step the "
                             "cameras + target images come from pinned host memory, the loss is read back"},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels_ms": kernels,
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels_ms": kernels, "variants": variants,
             "cpu_baseline": cpu_baseline, "reference_cuda": reference_cuda, "wall_ms_timed_region": round(wall_ms, 1),
         }
         if args.impl == "reference":
@@ -555,6 +712,10 @@ def main():
 def cpu_oracle_fps(scene, vms_h, pms_h, cps_h, RES, nframes, dLc, dLo):
     from oracle import surfel_oracle as so
     so.lib()
+    # one untimed warm-up frame (page faults of the oracle's buffers, OpenMP thread start-up), then the sample
+    st = so.forward(scene.means3D, scene.opacities, scene.scales, scene.rotations, shs=scene.shs, sh_degree=3, W=RES, H=RES,
+                    tanfovx=TAN, tanfovy=TAN, bg=(0, 0, 0), viewmatrix=vms_h[63], projmatrix=pms_h[63], campos=cps_h[63])
+    so.backward(st, dLc, dLo)
     t0 = time.perf_counter()
     for f in range(nframes):
         st = so.forward(scene.means3D, scene.opacities, scene.scales, scene.rotations, shs=scene.shs, sh_degree=3, W=RES, H=RES,
@@ -562,7 +723,7 @@ def cpu_oracle_fps(scene, vms_h, pms_h, cps_h, RES, nframes, dLc, dLo):
         so.backward(st, dLc, dLo)
     dt = time.perf_counter() - t0
     return {"value": round(nframes / dt, 4), "unit": "frames/s", "cores": so.num_threads(), "kind": "port",
-            "sample": f"{nframes} full frames of the same workload (fwd+bwd), oracle/surfel_oracle.c with OpenMP"}
+            "sample": f"{nframes} full frames of the same workload (fwd+bwd) after 1 warm-up frame, oracle/surfel_oracle.c with OpenMP"}
 
 
 def reference_cpu_arm(args, rank, world):
@@ -574,7 +735,7 @@ def reference_cpu_arm(args, rank, world):
     rng = np.random.default_rng(0)
     dLc = rng.normal(size=(3, args.res, args.res)).astype(np.float32)
     dLo = (0.1 * rng.normal(size=(8, args.res, args.res))).astype(np.float32)
-    n = max(1, min(args.steps, 4))
+    n = max(2, min(args.steps, 8))
     cb = cpu_oracle_fps(scene, vms_h, pms_h, cps_h, args.res, n, dLc, dLo)
     line = {"metric": "raster fwd+bwd frames/sec @512^2, 300K surfels", "value": cb["value"], "unit": "frames/s",
             "n_gpus": args.gpus, "steps": n, "warmup": 0, "ms_per_step": round(1e3 / cb["value"], 2), "higher_is_better": True,

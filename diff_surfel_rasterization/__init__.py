@@ -4,8 +4,8 @@ repository's root is on sys.path ahead of the reference package."""
 from vidu4d_b200.rasterizer import (  # noqa: F401
     GaussianRasterizationSettings,
     GaussianRasterizer,
-    _C,
     _RasterizeGaussians,
     cpu_deep_copy_tuple,
     rasterize_gaussians,
 )
+from . import _C  # noqa: F401  (importable submodule, like the reference's pybind extension)

@@ -129,12 +129,18 @@ SR_API int sr_backward(const sr_frame* f,
  * geom/binning/image buffers are M consecutive per-frame buffers of sr_*_bytes() each (same capacity for every frame);
  * num_rendered_dev / num_rendered_host are uint32[M*2] = {num_rendered, status} per frame.  Per-surfel inputs are
  * addressed as base + frame * stride (in floats; sr_batch), stride 0 = shared by all frames.  background[3] is shared.
- * Backward: dL_dout_color[M*3*H*W], dL_dout_others[M*8*H*W]; every gradient output is written per frame, (M, P, .);
+ * Backward: dL_dout_color[M*3*H*W], dL_dout_others[M*8*H*W]; every gradient output is written per frame, (M, P, .)
+ * -- except, with SR_BATCH_SUM_SHARED, those of shared inputs, which are (P, .) sums over the frames; dL_dmeans2D is always
+ * per frame; dL_dtransMat may be NULL in the batched call (it is only a by-product);
  * grad_scale (optional DEVICE scalar, NULL = 1) multiplies dL_dout_* -- the upstream scalar of a fused loss.
  * sr_forward / sr_backward are the M = 1 case.
  */
+#define SR_BATCH_SUM_SHARED 1u   /* backward: an input shared by the frames (stride 0) gets ONE gradient (P, .), the sum over
+                                    the frames, accumulated inside the per-surfel kernel and written once -- instead of
+                                    (M, P, .) per-frame gradients the caller would have to reduce */
 typedef struct sr_batch {
     int32_t frames;                                   /* M >= 1 */
+    uint32_t flags;                                   /* SR_BATCH_* */
     int64_t means3D, shs, colors_precomp, opacities, scales, rotations;   /* floats between consecutive frames; 0 = shared */
 } sr_batch;
 
@@ -175,10 +181,12 @@ typedef struct sr_debug_layout {
     size_t values[2];       /* uint32[capacity] x2 */
     size_t sort_ctl;        /* uint32[..]: [0]=sorted_sel (0/1) after forward */
     size_t inst_rec;        /* float[capacity*20] per-instance record stream */
+    size_t contrib;         /* uint32[((capacity>>5)+tiles+1)*256] per (32-instance stage, 8x4 sub-tile, pixel) contribution masks */
     /* image buffer */
     size_t final_T;         /* float[3*N]  T, M1, M2 */
     size_t n_contrib;       /* uint32[2*N] last, median */
     size_t ranges;          /* uint32[tiles*2] */
+    size_t sub_last;        /* uint32[tiles*8] deepest contributor (list position + 1) per 8x4 sub-tile */
 } sr_debug_layout;
 SR_API int sr_debug_view(int32_t P, int32_t width, int32_t height, int64_t capacity, sr_debug_layout* out);
 

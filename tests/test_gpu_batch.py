@@ -62,6 +62,21 @@ def test_batch_equals_single_frame_calls(per_frame, dev):
         for a, b in zip(gs, grads):
             assert a.shape == b[f].shape
             assert float((a - b[f]).abs().max()) <= 2e-5 * float(a.abs().max() + 1e-30)
+    # SR_BATCH_SUM_SHARED: gradients of inputs shared by the frames come back summed over the frames, in the input's shape
+    flat = torch.zeros((P * 48 + 64,), device=dev)
+    gsum = C.rasterize_gaussians_backward_batch(bg, means, radii, e, t["scales"], rots, 1.0, vms, pms, 0.5, 0.5, dLc, dLo, t["shs"],
+                                                3, cps, gb, bb, ib, sum_shared=True, want_transmat=False,
+                                                outs={"dL_dsh": flat[64:64 + P * 48]})
+    names = ("dL_dmeans2D", "dL_dcolors", "dL_dopacity", "dL_dmeans3D", "dL_dtransMat", "dL_dsh", "dL_dscales", "dL_drotations")
+    per_frame_inputs = {"dL_dmeans2D"} | ({"dL_dmeans3D", "dL_drotations"} if per_frame else set())
+    for nme, a, b in zip(names, grads, gsum):
+        if nme == "dL_dtransMat":
+            assert b is None
+            continue
+        want = a if nme in per_frame_inputs else a.sum(0)
+        assert b.shape == want.shape, nme
+        assert float((b - want).abs().max()) <= 2e-5 * float(want.abs().max() + 1e-30), nme
+    assert gsum[5].data_ptr() == flat[64:].data_ptr()           # written in place into the caller's buffer
     # grad_scale: the backward is linear in dL_dout
     g2 = C.rasterize_gaussians_backward_batch(bg, means, radii, e, t["scales"], rots, 1.0, vms, pms, 0.5, 0.5, dLc, dLo, t["shs"],
                                               3, cps, gb, bb, ib, grad_scale=torch.tensor(-2.5, device=dev))

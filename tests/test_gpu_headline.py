@@ -58,11 +58,16 @@ def test_headline_against_live_reference(view, dev):
                        (r["point_list"], ref["bin_point_list"], "sorted surfel ids"), (r["ranges"], ref["img_ranges"], "tile ranges")):
         np.testing.assert_array_equal(_np(a), b, err_msg=what)
     _assert_n_contrib(_np(r["n_contrib"]), ref["img_n_contrib"], ref["img_ranges"], 512, 512)
-    # ---- rendered planes: 1e-4 relative (colour is expected bit-identical: same FMA map as the reference build)
-    assert np.array_equal(_np(r["color"]), ref["color"])
+    # ---- rendered planes: 1e-4 relative (north_star).  Observed: depth/alpha/normal/median planes bit-identical; colour
+    # within 1 ulp on ~0.1 % of the pixels (the SH -> RGB evaluation of a surfel is value-level, not FMA-mapped, since
+    # no binning decision depends on it), distortion within 1e-7 (fp32 depth mapping).  Assert a
+    # bound 100x tighter than the contract so that a real regression cannot hide.
+    assert np.abs(_np(r["color"]) - ref["color"]).max() <= 1e-6 * max(1.0, np.abs(ref["color"]).max())
     am, rm = _np(r["allmap"]), ref["allmap"]
     for ch in range(8):
         assert np.abs(am[ch] - rm[ch]).max() <= TOL * max(np.abs(rm[ch]).max(), 1e-30), f"allmap[{ch}]"
+    for ch in (0, 1, 2, 3, 4, 5, 7):
+        assert np.array_equal(am[ch], rm[ch]), f"allmap[{ch}] is expected bit-identical to the reference build"
     # ---- all eight gradient tensors: 1e-4 of the tensor's max magnitude
     for k in GRADS:
         b = ref["grad_" + k]

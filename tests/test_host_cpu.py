@@ -88,6 +88,17 @@ def test_api_surface_matches_reference_names():
     assert hasattr(R.GaussianRasterizer, "markVisible")
 
 
+def test_C_is_an_importable_submodule():
+    """`from diff_surfel_rasterization import _C` and `import diff_surfel_rasterization._C` both work, as with the
+    reference's pybind extension (RAST/setup.py:18-23, RAST/diff_surfel_rasterization/__init__.py:14)."""
+    import importlib
+    m = importlib.import_module("diff_surfel_rasterization._C")
+    from diff_surfel_rasterization import _C
+    assert m is _C
+    for fn in ("rasterize_gaussians", "rasterize_gaussians_backward", "mark_visible"):
+        assert callable(getattr(m, fn))
+
+
 def test_rasterizer_argument_errors_match_reference():
     from vidu4d_b200.rasterizer import GaussianRasterizationSettings, GaussianRasterizer
     rs = GaussianRasterizationSettings(8, 8, 0.5, 0.5, torch.zeros(3), 1.0, torch.eye(4), torch.eye(4), 0,

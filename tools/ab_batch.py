@@ -29,6 +29,21 @@ flush = torch.empty((256 << 20,), dtype=torch.uint8, device=dev)
 def step(s):
     v0 = (s * F) %% 64
     idx = [(v0 + f) %% 64 for f in range(F)]
+    if mode == "split":      # S half-/quarter-batches on S streams
+        main = torch.cuda.current_stream()
+        for st in side: st.wait_stream(main)
+        n = F // S
+        for k in range(S):
+            with torch.cuda.stream(side[k]):
+                ii = idx[k * n:(k + 1) * n]
+                o = C.rasterize_gaussians_batch(bg, t["means3D"], e, t["opacities"], t["scales"], t["rotations"], 1.0, vms[ii], pms[ii], 0.5, 0.5, res, res, t["shs"], 3, cps[ii])
+                gr = C.rasterize_gaussians_backward_batch(bg, t["means3D"], o[3], e, t["scales"], t["rotations"], 1.0, vms[ii], pms[ii], 0.5, 0.5, dLc[k * n:(k + 1) * n], dLo[k * n:(k + 1) * n], t["shs"], 3, cps[ii], o[4], o[5], o[6], sum_shared=True, want_transmat=False)
+        for st in side: main.wait_stream(st)
+        return o, gr
+    if mode == "batchsum":
+        o = C.rasterize_gaussians_batch(bg, t["means3D"], e, t["opacities"], t["scales"], t["rotations"], 1.0, vms[idx], pms[idx], 0.5, 0.5, res, res, t["shs"], 3, cps[idx])
+        gr = C.rasterize_gaussians_backward_batch(bg, t["means3D"], o[3], e, t["scales"], t["rotations"], 1.0, vms[idx], pms[idx], 0.5, 0.5, dLc, dLo, t["shs"], 3, cps[idx], o[4], o[5], o[6], sum_shared=True, want_transmat=False)
+        return o, gr
     if mode == "batch":
         o = C.rasterize_gaussians_batch(bg, t["means3D"], e, t["opacities"], t["scales"], t["rotations"], 1.0, vms[idx], pms[idx], 0.5, 0.5, res, res, t["shs"], 3, cps[idx])
         gr = C.rasterize_gaussians_backward_batch(bg, t["means3D"], o[3], e, t["scales"], t["rotations"], 1.0, vms[idx], pms[idx], 0.5, 0.5, dLc, dLo, t["shs"], 3, cps[idx], o[4], o[5], o[6])

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libsurfel_raster.so")
 ABI_VERSION = 3
 SR_STATUS_OVERFLOW = 1
 SR_STATUS_PREFILTER = 4
+SR_BATCH_SUM_SHARED = 1
 
 SYMBOLS = (
     "sr_geom_bytes", "sr_image_bytes", "sr_binning_bytes", "sr_forward", "sr_backward",
@@ -33,7 +34,7 @@ class SrFrame(C.Structure):
 
 class SrBatch(C.Structure):
     """sr_batch: frames + per-frame strides (in floats; 0 = shared by all frames) of the per-surfel inputs."""
-    _fields_ = [("frames", C.c_int32), ("means3D", C.c_int64), ("shs", C.c_int64), ("colors_precomp", C.c_int64),
+    _fields_ = [("frames", C.c_int32), ("flags", C.c_uint32), ("means3D", C.c_int64), ("shs", C.c_int64), ("colors_precomp", C.c_int64),
                 ("opacities", C.c_int64), ("scales", C.c_int64), ("rotations", C.c_int64)]
 
 
@@ -42,8 +43,8 @@ class SrDebugLayout(C.Structure):
         ("surfel_rec", C.c_size_t), ("depths", C.c_size_t), ("tiles_touched", C.c_size_t),
         ("point_offsets", C.c_size_t), ("clamped", C.c_size_t),
         ("keys", C.c_size_t * 2), ("values", C.c_size_t * 2), ("sort_ctl", C.c_size_t),
-        ("inst_rec", C.c_size_t),
-        ("final_T", C.c_size_t), ("n_contrib", C.c_size_t), ("ranges", C.c_size_t),
+        ("inst_rec", C.c_size_t), ("contrib", C.c_size_t),
+        ("final_T", C.c_size_t), ("n_contrib", C.c_size_t), ("ranges", C.c_size_t), ("sub_last", C.c_size_t),
     ]
 
 

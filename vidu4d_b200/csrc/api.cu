@@ -136,8 +136,8 @@ int sr_debug_view(int32_t P, int32_t width, int32_t height, int64_t capacity, sr
     out->surfel_rec = g.surfel_rec; out->depths = g.depths; out->tiles_touched = g.tiles_touched;
     out->point_offsets = g.point_offsets; out->clamped = g.clamped;
     out->keys[0] = b.keys[0]; out->keys[1] = b.keys[1]; out->values[0] = b.values[0]; out->values[1] = b.values[1];
-    out->sort_ctl = b.sort_ctl; out->inst_rec = b.inst_rec;
-    out->final_T = i.final_T; out->n_contrib = i.n_contrib; out->ranges = i.ranges;
+    out->sort_ctl = b.sort_ctl; out->inst_rec = b.inst_rec; out->contrib = b.contrib;
+    out->final_T = i.final_T; out->n_contrib = i.n_contrib; out->ranges = i.ranges; out->sub_last = i.tile_last;
     return 0;
 }
 
@@ -203,7 +203,7 @@ int sr_forward_batch(const sr_frame* f, const sr_batch* b, const float* backgrou
     CK(launch_sort(a), "sort"); DBG("sort");
     CK(launch_ranges_gather(a), "ranges_gather"); DBG("ranges_gather");
     CK(launch_tile_order(a), "tile_order"); DBG("tile_order");
-    if (sr_composite_tile_mode()) { CK(launch_composite_tile_fwd(a), "composite_tile_fwd"); }
+    if (sr_composite_tile_mode(false)) { CK(launch_composite_tile_fwd(a), "composite_tile_fwd"); }
     else { CK(launch_composite_fwd(a), "composite_fwd"); }
     DBG("composite_fwd");
     if (num_rendered_host)
@@ -216,7 +216,7 @@ int sr_forward(const sr_frame* f, const float* background, const float* means3D,
                const float* viewmatrix, const float* projmatrix, const float* campos, float* out_color,
                float* out_others, int32_t* radii, void* geom_buffer, void* binning_buffer, void* image_buffer,
                int64_t capacity, uint32_t* num_rendered_dev, uint32_t* num_rendered_host, void* stream_) {
-    const sr_batch one = {1, 0, 0, 0, 0, 0, 0};
+    const sr_batch one = {1, 0u, 0, 0, 0, 0, 0, 0};
     return sr_forward_batch(f, &one, background, means3D, shs, colors_precomp, opacities, scales, rotations, viewmatrix,
                             projmatrix, campos, out_color, out_others, radii, geom_buffer, binning_buffer, image_buffer,
                             capacity, num_rendered_dev, num_rendered_host, stream_);
@@ -238,8 +238,9 @@ int sr_backward_batch(const sr_frame* f, const sr_batch* b, const float* backgro
     if (!background || !means3D || !scales || !rotations || !viewmatrix || !campos || !radii || !dL_dout_color ||
         !dL_dout_others || !geom_buffer || !binning_buffer || !image_buffer)
         return fail(SR_EINVAL, "input pointer is NULL");
-    if (!dL_dmeans2D || !dL_dcolors || !dL_dopacity || !dL_dmeans3D || !dL_dtransMat || !dL_dscales || !dL_drotations)
+    if (!dL_dmeans2D || !dL_dcolors || !dL_dopacity || !dL_dmeans3D || !dL_dscales || !dL_drotations)
         return fail(SR_EINVAL, "gradient output pointer is NULL");
+    if (!dL_dtransMat && b->frames == 1 && !(b->flags & SR_BATCH_SUM_SHARED)) return fail(SR_EINVAL, "dL_dtransMat is NULL");
     if (shs && !dL_dsh) return fail(SR_EINVAL, "dL_dsh is NULL");
     if (capacity <= 0) return fail(SR_EINVAL, "capacity must be positive");
     if (((uintptr_t)rotations & 15) || ((uintptr_t)scales & 7) || (shs && ((uintptr_t)shs & 15)) ||
@@ -267,11 +268,18 @@ int sr_backward_batch(const sr_frame* f, const sr_batch* b, const float* backgro
     fs.scales = b->scales * 4; fs.rots = b->rotations * 4; fs.vm = 16 * sizeof(float); fs.campos = 3 * sizeof(float);
     fs.radii = (long long)P * sizeof(int32_t);
     fs.dcolor = (long long)(3 * N * sizeof(float)); fs.dothers = (long long)(8 * N * sizeof(float));
-    // gradients are written per frame: (M, P, .) each
+    // gradients are written per frame, (M, P, .) -- or, with SR_BATCH_SUM_SHARED, once as the sum over frames, (P, .), for
+    // the inputs the frames share (surfel_bwd.cu accumulates them inside the kernel; stride 0 selects that)
     const long long Pl = P;
-    fs.g_m2d = Pl * 3 * 4; fs.g_col = Pl * 3 * 4; fs.g_opac = Pl * 4; fs.g_m3d = Pl * 3 * 4; fs.g_tm = Pl * 9 * 4;
-    fs.g_sh = Pl * a.cam.M * 3 * 4; fs.g_scales = Pl * 2 * 4; fs.g_rots = Pl * 4 * 4;
-    if (sr_composite_tile_mode()) { CK(launch_composite_tile_bwd(a), "composite_tile_bwd"); }
+    const bool sum = (b->flags & SR_BATCH_SUM_SHARED) != 0 && M > 1;
+    fs.g_m2d = Pl * 3 * 4; fs.g_tm = Pl * 9 * 4;
+    fs.g_col = (sum && b->colors_precomp == 0) ? 0 : Pl * 3 * 4;
+    fs.g_opac = (sum && b->opacities == 0) ? 0 : Pl * 4;
+    fs.g_m3d = (sum && b->means3D == 0) ? 0 : Pl * 3 * 4;
+    fs.g_sh = (sum && b->shs == 0) ? 0 : Pl * a.cam.M * 3 * 4;
+    fs.g_scales = (sum && b->scales == 0) ? 0 : Pl * 2 * 4;
+    fs.g_rots = (sum && b->rotations == 0) ? 0 : Pl * 4 * 4;
+    if (sr_composite_tile_mode(true)) { CK(launch_composite_tile_bwd(a), "composite_tile_bwd"); }
     else { CK(launch_composite_bwd(a), "composite_bwd"); }
     DBG("composite_bwd");
     CK(launch_surfel_bwd(a), "surfel_bwd"); DBG("surfel_bwd");
@@ -284,7 +292,7 @@ int sr_backward(const sr_frame* f, const float* background, const float* means3D
                 const float* dL_dout_others, void* geom_buffer, void* binning_buffer, void* image_buffer,
                 int64_t capacity, float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity, float* dL_dmeans3D,
                 float* dL_dtransMat, float* dL_dsh, float* dL_dscales, float* dL_drotations, void* stream_) {
-    const sr_batch one = {1, 0, 0, 0, 0, 0, 0};
+    const sr_batch one = {1, 0u, 0, 0, 0, 0, 0, 0};
     return sr_backward_batch(f, &one, background, means3D, shs, colors_precomp, scales, rotations, viewmatrix, projmatrix,
                              campos, radii, dL_dout_color, dL_dout_others, nullptr, geom_buffer, binning_buffer, image_buffer,
                              capacity, dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dtransMat, dL_dsh, dL_dscales,

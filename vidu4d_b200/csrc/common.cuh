@@ -199,7 +199,7 @@ cudaError_t launch_composite_bwd(const BwdArgs& a);       // composite_bwd.cu
 cudaError_t launch_surfel_bwd(const BwdArgs& a);          // surfel_bwd.cu
 cudaError_t launch_composite_tile_fwd(const FwdArgs& a);  // composite_tile.cu (one CTA per tile, shared chunk ring)
 cudaError_t launch_composite_tile_bwd(const BwdArgs& a);  // composite_tile.cu
-bool sr_composite_tile_mode();                            // SURFEL_COMPOSITE=tile|warp (default: tile)
+bool sr_composite_tile_mode(bool backward);               // SURFEL_COMPOSITE[_FWD|_BWD]=tile|warp
 cudaError_t launch_mark_visible(int P, const float* means3D, const float* vm, uint8_t* present, cudaStream_t s);
 // clears `bytes` at p + f * pitch for every frame f of the batch (one 2-D memset)
 cudaError_t sr_memset_frames(void* p, size_t pitch, size_t bytes, int frames, cudaStream_t s);

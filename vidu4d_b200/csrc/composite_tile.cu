@@ -30,9 +30,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"     // suspend-time hint: the warp sleeps in hardware
+        "selp.u32 %0, 1, 0, p;\n"                                          // instead of spinning (r2a ncu: 8 % of the
+        "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");   // forward's issue slots were the spin loop)
     return ok != 0;
 }
 
@@ -376,9 +376,20 @@ cudaError_t opt_in_smem(K kern, size_t bytes) {
 
 }  // namespace
 
-bool sr_composite_tile_mode() {
-    static const bool tile = [] { const char* e = getenv("SURFEL_COMPOSITE"); return !(e && e[0] == 'w'); }();
-    return tile;
+// Which composite kernels run: SURFEL_COMPOSITE=tile|warp sets both directions, SURFEL_COMPOSITE_FWD / _BWD one of them.
+// Defaults (measured on the headline batch, profiles/README.md r2): forward = one-warp CTAs with private rings (fewer
+// instructions per iteration; the forward is issue bound), backward = tile CTAs with the shared chunk ring (25 % fewer
+// instructions thanks to the per-lane free walk; the backward is bound by L2 reductions and latency).
+bool sr_composite_tile_mode(bool backward) {
+    static const int mode = [] {
+        auto pick = [](const char* name, int dflt) {
+            const char* e = getenv(name);
+            if (!e) e = getenv("SURFEL_COMPOSITE");
+            return e ? (e[0] == 't' ? 1 : 0) : dflt;
+        };
+        return pick("SURFEL_COMPOSITE_FWD", 0) | (pick("SURFEL_COMPOSITE_BWD", 1) << 1);
+    }();
+    return backward ? (mode >> 1) & 1 : mode & 1;
 }
 
 int comp::tile_cfg_from_env() {

@@ -31,19 +31,56 @@ __device__ __forceinline__ V3 wtmul(const float* m, V3 v) {     // W^T * v
     return {m[0] * v.x + m[1] * v.y + m[2] * v.z, m[4] * v.x + m[5] * v.y + m[6] * v.z, m[8] * v.x + m[9] * v.y + m[10] * v.z};
 }
 
+// one surfel's gradients for one frame (everything except dL/dSH, which goes through the shared-memory row)
+struct SurfelGrad {
+    float m2d[3], col[3], op, m3d[3], tm[9], sc[2], rot[4];
+};
+
+template <bool ACC>
 __device__ __forceinline__ void
-surfel_bwd_body(const CamParams& c, const int idx, const int M, float* osh, const float* __restrict__ means3D, const bool has_sh,
-                const float2* __restrict__ scales, const float4* __restrict__ rotations, const int* __restrict__ radii,
+surfel_bwd_body(const CamParams& c, const int idx, const int M, const float* shv, float* shg, const float* __restrict__ means3D,
+                const bool has_sh, const float2* __restrict__ scales, const float4* __restrict__ rotations,
                 const float4* __restrict__ srec, const uint8_t* __restrict__ clamped, const float4* __restrict__ sgrad,
-                float* __restrict__ dL_dmeans2D, float* __restrict__ dL_dcolors, float* __restrict__ dL_dopacity,
-                float* __restrict__ dL_dmeans3D, float* __restrict__ dL_dtransMat,
-                float2* __restrict__ dL_dscales, float4* __restrict__ dL_drotations);
+                SurfelGrad& G);
 
 // Block = 128 surfels.  The block's SH coefficients (128 x 3M floats, contiguous in HBM) are pulled into shared
-// memory with coalesced 128-bit loads, each thread works on its own padded row (stride 3M+1: conflict-free),
-// overwrites it with dL/dSH, and the block streams the rows back out coalesced -- instead of 48 scalar loads and
-// 48 scalar stores per thread at a 192-byte lane stride (r1a: 118 us for 175 MB).
+// memory with coalesced 128-bit loads, each thread works on its own padded rows (stride 3M+1: conflict-free) -- one
+// row of SH values, one of dL/dSH -- and the block streams the gradient rows back out coalesced, instead of 48 scalar
+// loads and 48 scalar stores per thread at a 192-byte lane stride (r1a: 118 us for 175 MB).
+//
+// Batches: the kernel loops over the frames INSIDE the thread.  An input that is shared by the frames of a batch
+// (stride 0: in Stage 3 everything except positions and orientations) gets ONE gradient, the sum over frames,
+// accumulated in registers / in the shared-memory row and written once -- the (M, P, 48) dL/dSH tensor and the torch
+// reduction over M that would follow never exist.  Per-frame inputs get per-frame gradients.
 constexpr int SB = 128;
+
+__device__ __forceinline__ void stage_rows_in(float* dst, const float* __restrict__ gsrc, int nrows, int M3, int stride) {
+    const int total = nrows * M3;
+    if ((M3 & 3) == 0) {
+        const float4* g4 = reinterpret_cast<const float4*>(gsrc);
+        for (int i = threadIdx.x; i < total / 4; i += SB) {
+            const float4 v = __ldg(g4 + i);
+            const int e = i * 4, r = e / M3, col = e - r * M3;     // 4 | M3 => the four stay in one row
+            float* d = dst + r * stride + col;
+            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        }
+    } else {
+        for (int i = threadIdx.x; i < total; i += SB) { const int r = i / M3; dst[r * stride + (i - r * M3)] = __ldg(gsrc + i); }
+    }
+}
+__device__ __forceinline__ void stage_rows_out(float* __restrict__ gdst, const float* src, int nrows, int M3, int stride) {
+    const int total = nrows * M3;
+    if ((M3 & 3) == 0) {
+        float4* g4 = reinterpret_cast<float4*>(gdst);
+        for (int i = threadIdx.x; i < total / 4; i += SB) {
+            const int e = i * 4, r = e / M3, col = e - r * M3;
+            const float* d = src + r * stride + col;
+            g4[i] = make_float4(d[0], d[1], d[2], d[3]);
+        }
+    } else {
+        for (int i = threadIdx.x; i < total; i += SB) { const int r = i / M3; gdst[i] = src[r * stride + (i - r * M3)]; }
+    }
+}
 
 __global__ void __launch_bounds__(SB)
 surfel_bwd_kernel(const CamParams c_, const FrameStrides fs, const float* __restrict__ means3D, const float* __restrict__ shs,
@@ -53,73 +90,91 @@ surfel_bwd_kernel(const CamParams c_, const FrameStrides fs, const float* __rest
                   float* __restrict__ dL_dmeans3D, float* __restrict__ dL_dtransMat, float* __restrict__ dL_dsh,
                   float2* __restrict__ dL_dscales, float4* __restrict__ dL_drotations) {
     extern __shared__ float shbuf[];
-    const int f = blockIdx.y;                       // frame of the batch
-    const CamParams c = cam_of_frame(c_, fs, f);
-    means3D = fr(means3D, fs.means3D, f); shs = fr(shs, fs.shs, f); scales = fr(scales, fs.scales, f);
-    rotations = fr(rotations, fs.rots, f); radii = fr(radii, fs.radii, f); srec = fr(srec, fs.geom, f);
-    clamped = fr(clamped, fs.geom, f); sgrad = fr(sgrad, fs.geom, f);
-    dL_dmeans2D = fr(dL_dmeans2D, fs.g_m2d, f); dL_dcolors = fr(dL_dcolors, fs.g_col, f); dL_dopacity = fr(dL_dopacity, fs.g_opac, f);
-    dL_dmeans3D = fr(dL_dmeans3D, fs.g_m3d, f); dL_dtransMat = fr(dL_dtransMat, fs.g_tm, f); dL_dsh = fr(dL_dsh, fs.g_sh, f);
-    dL_dscales = fr(dL_dscales, fs.g_scales, f); dL_drotations = fr(dL_drotations, fs.g_rots, f);
-    const int M = c.M, M3 = 3 * c.M, stride = M3 + 1;
+    const int M = c_.M, M3 = 3 * M, stride = M3 + 1;
     const int idx = blockIdx.x * SB + threadIdx.x;
     const int base = blockIdx.x * SB;
-    const int nrows = min(SB, c.P - base);
-    if (shs != nullptr) {
-        const float* gsrc = shs + (size_t)base * M3;
-        const int total = nrows * M3;
-        if ((M3 & 3) == 0) {
-            const float4* g4 = reinterpret_cast<const float4*>(gsrc);
-            for (int i = threadIdx.x; i < total / 4; i += SB) {
-                const float4 v = __ldg(g4 + i);
-                const int e = i * 4, r = e / M3, col = e - r * M3;     // 4 | M3 => the four stay in one row
-                float* d = shbuf + r * stride + col;
-                d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    const int nrows = min(SB, c_.P - base);
+    const bool has_sh = shs != nullptr;
+    float* shv_all = shbuf;                          // SH values      [SB][stride]
+    float* shg_all = shbuf + SB * stride;            // dL/dSH         [SB][stride]
+    float* shv = shv_all + threadIdx.x * stride;
+    float* shg = shg_all + threadIdx.x * stride;
+    // which gradients are sums over the frames (their input is shared by the batch)
+    const bool multi = fs.frames > 1;
+    const bool sum_sh = multi && fs.g_sh == 0, sum_m3d = multi && fs.g_m3d == 0, sum_op = multi && fs.g_opac == 0;
+    const bool sum_sc = multi && fs.g_scales == 0, sum_rot = multi && fs.g_rots == 0, sum_col = multi && fs.g_col == 0;
+    float a_m3d[3] = {0.f, 0.f, 0.f}, a_col[3] = {0.f, 0.f, 0.f}, a_op = 0.f, a_sc[2] = {0.f, 0.f}, a_rot[4] = {0.f, 0.f, 0.f, 0.f};
+    if (has_sh && sum_sh) for (int i = 0; i < M3; i++) shg[i] = 0.f;
+
+    for (int f = 0; f < fs.frames; f++) {
+        const CamParams c = cam_of_frame(c_, fs, f);
+        if (has_sh && (f == 0 || fs.shs != 0)) {
+            __syncthreads();                         // previous frame's readers of shv are done
+            stage_rows_in(shv_all, fr(shs, fs.shs, f) + (size_t)base * M3, nrows, M3, stride);
+            __syncthreads();
+        }
+        if (idx < c.P) {
+            SurfelGrad G;
+            const bool vis = fr(radii, fs.radii, f)[idx] > 0;
+            if (vis) {
+                if (sum_sh)
+                    surfel_bwd_body<true>(c, idx, M, shv, shg, fr(means3D, fs.means3D, f), has_sh, fr(scales, fs.scales, f),
+                                          fr(rotations, fs.rots, f), fr(srec, fs.geom, f), fr(clamped, fs.geom, f), fr(sgrad, fs.geom, f), G);
+                else
+                    surfel_bwd_body<false>(c, idx, M, shv, shg, fr(means3D, fs.means3D, f), has_sh, fr(scales, fs.scales, f),
+                                           fr(rotations, fs.rots, f), fr(srec, fs.geom, f), fr(clamped, fs.geom, f), fr(sgrad, fs.geom, f), G);
+            } else {
+                // invisible in this frame: every gradient is zero (the reference leaves its zero-filled tensors untouched)
+#pragma unroll
+                for (int i = 0; i < 3; i++) { G.m2d[i] = 0.f; G.col[i] = 0.f; G.m3d[i] = 0.f; }
+                G.op = 0.f; G.sc[0] = G.sc[1] = 0.f;
+#pragma unroll
+                for (int i = 0; i < 4; i++) G.rot[i] = 0.f;
+#pragma unroll
+                for (int i = 0; i < 9; i++) G.tm[i] = 0.f;
+                if (has_sh && !sum_sh) for (int i = 0; i < M3; i++) shg[i] = 0.f;
             }
-        } else {
-            for (int i = threadIdx.x; i < total; i += SB) { const int r = i / M3; shbuf[r * stride + (i - r * M3)] = __ldg(gsrc + i); }
+            // ---- per-frame outputs are written now, shared ones accumulate
+            float* o2d = fr(dL_dmeans2D, fs.g_m2d, f) + 3 * (size_t)idx;
+            o2d[0] = G.m2d[0]; o2d[1] = G.m2d[1]; o2d[2] = G.m2d[2];
+            if (dL_dtransMat != nullptr) {
+                float* otm = fr(dL_dtransMat, fs.g_tm, f) + 9 * (size_t)idx;
+#pragma unroll
+                for (int i = 0; i < 9; i++) otm[i] = G.tm[i];
+            }
+            if (sum_m3d) { a_m3d[0] += G.m3d[0]; a_m3d[1] += G.m3d[1]; a_m3d[2] += G.m3d[2]; }
+            else { float* o = fr(dL_dmeans3D, fs.g_m3d, f) + 3 * (size_t)idx; o[0] = G.m3d[0]; o[1] = G.m3d[1]; o[2] = G.m3d[2]; }
+            if (sum_col) { a_col[0] += G.col[0]; a_col[1] += G.col[1]; a_col[2] += G.col[2]; }
+            else { float* o = fr(dL_dcolors, fs.g_col, f) + 3 * (size_t)idx; o[0] = G.col[0]; o[1] = G.col[1]; o[2] = G.col[2]; }
+            if (sum_op) a_op += G.op; else fr(dL_dopacity, fs.g_opac, f)[idx] = G.op;
+            if (sum_sc) { a_sc[0] += G.sc[0]; a_sc[1] += G.sc[1]; } else fr(dL_dscales, fs.g_scales, f)[idx] = make_float2(G.sc[0], G.sc[1]);
+            if (sum_rot) { a_rot[0] += G.rot[0]; a_rot[1] += G.rot[1]; a_rot[2] += G.rot[2]; a_rot[3] += G.rot[3]; }
+            else fr(dL_drotations, fs.g_rots, f)[idx] = make_float4(G.rot[0], G.rot[1], G.rot[2], G.rot[3]);
+        }
+        if (has_sh && !sum_sh) {
+            __syncthreads();
+            stage_rows_out(fr(dL_dsh, fs.g_sh, f) + (size_t)base * M3, shg_all, nrows, M3, stride);
         }
     }
-    __syncthreads();
-    float* osh = shbuf + threadIdx.x * stride;      // this thread's row: SH in, dL/dSH out
-    if (idx < c.P) surfel_bwd_body(c, idx, M, osh, means3D, shs != nullptr, scales, rotations, radii, srec, clamped, sgrad,
-                                   dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dtransMat, dL_dscales, dL_drotations);
-    __syncthreads();
-    if (shs != nullptr) {
-        float* gdst = dL_dsh + (size_t)base * M3;
-        const int total = nrows * M3;
-        if ((M3 & 3) == 0) {
-            float4* g4 = reinterpret_cast<float4*>(gdst);
-            for (int i = threadIdx.x; i < total / 4; i += SB) {
-                const int e = i * 4, r = e / M3, col = e - r * M3;
-                const float* d = shbuf + r * stride + col;
-                g4[i] = make_float4(d[0], d[1], d[2], d[3]);
-            }
-        } else {
-            for (int i = threadIdx.x; i < total; i += SB) { const int r = i / M3; gdst[i] = shbuf[r * stride + (i - r * M3)]; }
-        }
+    if (idx < c_.P) {
+        if (sum_m3d) { float* o = dL_dmeans3D + 3 * (size_t)idx; o[0] = a_m3d[0]; o[1] = a_m3d[1]; o[2] = a_m3d[2]; }
+        if (sum_col) { float* o = dL_dcolors + 3 * (size_t)idx; o[0] = a_col[0]; o[1] = a_col[1]; o[2] = a_col[2]; }
+        if (sum_op) dL_dopacity[idx] = a_op;
+        if (sum_sc) dL_dscales[idx] = make_float2(a_sc[0], a_sc[1]);
+        if (sum_rot) dL_drotations[idx] = make_float4(a_rot[0], a_rot[1], a_rot[2], a_rot[3]);
+    }
+    if (has_sh && sum_sh) {
+        __syncthreads();
+        stage_rows_out(dL_dsh + (size_t)base * M3, shg_all, nrows, M3, stride);
     }
 }
 
+template <bool ACC>
 __device__ __forceinline__ void
-surfel_bwd_body(const CamParams& c, const int idx, const int M, float* osh, const float* __restrict__ means3D, const bool has_sh,
-                const float2* __restrict__ scales, const float4* __restrict__ rotations, const int* __restrict__ radii,
+surfel_bwd_body(const CamParams& c, const int idx, const int M, const float* shv, float* shg, const float* __restrict__ means3D,
+                const bool has_sh, const float2* __restrict__ scales, const float4* __restrict__ rotations,
                 const float4* __restrict__ srec, const uint8_t* __restrict__ clamped, const float4* __restrict__ sgrad,
-                float* __restrict__ dL_dmeans2D, float* __restrict__ dL_dcolors, float* __restrict__ dL_dopacity,
-                float* __restrict__ dL_dmeans3D, float* __restrict__ dL_dtransMat,
-                float2* __restrict__ dL_dscales, float4* __restrict__ dL_drotations) {
-    if (!(radii[idx] > 0)) {
-        // invisible: every gradient is zero (the reference leaves its zero-filled tensors untouched)
-#pragma unroll
-        for (int i = 0; i < 3; i++) { dL_dmeans2D[3 * (size_t)idx + i] = 0.f; dL_dcolors[3 * (size_t)idx + i] = 0.f; dL_dmeans3D[3 * (size_t)idx + i] = 0.f; }
-        dL_dopacity[idx] = 0.f;
-#pragma unroll
-        for (int i = 0; i < 9; i++) dL_dtransMat[9 * (size_t)idx + i] = 0.f;
-        for (int i = 0; i < M * 3; i++) osh[i] = 0.f;
-        dL_dscales[idx] = make_float2(0.f, 0.f);
-        dL_drotations[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
-        return;
-    }
+                SurfelGrad& G) {
     float vm[16];
 #pragma unroll
     for (int i = 0; i < 16; i++) vm[i] = __ldg(c.vm + i);
@@ -154,14 +209,14 @@ surfel_bwd_body(const CamParams& c, const int idx, const int M, float* osh, cons
         dT[8] += dL_dT3[2] + dL_dd * (-2.0f * T[8]);
     }
 #pragma unroll
-    for (int i = 0; i < 9; i++) dL_dtransMat[9 * (size_t)idx + i] = dT[i];
+    for (int i = 0; i < 9; i++) G.tm[i] = dT[i];
     // densification proxy that the reference stores into dL_dmean2D (backward.cu:645-648)
-    dL_dmeans2D[3 * (size_t)idx + 0] = dT[2] * T[8] * c.bcx;
-    dL_dmeans2D[3 * (size_t)idx + 1] = dT[5] * T[8] * c.bcy;
-    dL_dmeans2D[3 * (size_t)idx + 2] = 0.f;
-    dL_dopacity[idx] = dop;
+    G.m2d[0] = dT[2] * T[8] * c.bcx;
+    G.m2d[1] = dT[5] * T[8] * c.bcy;
+    G.m2d[2] = 0.f;
+    G.op = dop;
 #pragma unroll
-    for (int i = 0; i < 3; i++) dL_dcolors[3 * (size_t)idx + i] = dcol[i];
+    for (int i = 0; i < 3; i++) G.col[i] = dcol[i];
 
     // ---- computeTransMat vjp (backward.cu:451-529) ----
     const float4 q = __ldg(rotations + idx);
@@ -198,8 +253,9 @@ surfel_bwd_body(const CamParams& c, const int idx, const int M, float* osh, cons
     dq.y = 2.f * (-2.f * x * (vR[1][1] + vR[2][2]) + y * (vR[0][1] + vR[1][0]) + z * (vR[0][2] + vR[2][0]) + w * (vR[1][2] - vR[2][1]));
     dq.z = 2.f * (x * (vR[0][1] + vR[1][0]) - 2.f * y * (vR[0][0] + vR[2][2]) + z * (vR[1][2] + vR[2][1]) + w * (vR[2][0] - vR[0][2]));
     dq.w = 2.f * (x * (vR[0][2] + vR[2][0]) + y * (vR[1][2] + vR[2][1]) - 2.f * z * (vR[0][0] + vR[1][1]) + w * (vR[0][1] - vR[1][0]));
-    dL_drotations[idx] = dq;
-    dL_dscales[idx] = make_float2(dRS0.x * R[0] + dRS0.y * R[1] + dRS0.z * R[2], dRS1.x * R[3] + dRS1.y * R[4] + dRS1.z * R[5]);
+    G.rot[0] = dq.x; G.rot[1] = dq.y; G.rot[2] = dq.z; G.rot[3] = dq.w;
+    G.sc[0] = dRS0.x * R[0] + dRS0.y * R[1] + dRS0.z * R[2];
+    G.sc[1] = dRS1.x * R[3] + dRS1.y * R[4] + dRS1.z * R[5];
     float dmean[3] = {dpw.x, dpw.y, dpw.z};
 
     // ---- SH vjp (backward.cu:20-139) ----
@@ -213,10 +269,12 @@ surfel_bwd_body(const CamParams& c, const int idx, const int M, float* osh, cons
 #pragma unroll
         for (int ch = 0; ch < 3; ch++) dRGB[ch] = (cl >> ch) & 1u ? 0.f : dcol[ch];
         float ddx = 0.f, ddy = 0.f, ddz = 0.f;   // dL/ddir accumulated over channels
-#define SH(k, ch) osh[3 * (k) + (ch)]
-#define SETSH(k, wgt) { const float w_ = (wgt); osh[3 * (k)] = w_ * dRGB[0]; osh[3 * (k) + 1] = w_ * dRGB[1]; osh[3 * (k) + 2] = w_ * dRGB[2]; }
+#define SH(k, ch) shv[3 * (k) + (ch)]
+#define SETSH(k, wgt) { const float w_ = (wgt); \
+        if (ACC) { shg[3 * (k)] += w_ * dRGB[0]; shg[3 * (k) + 1] += w_ * dRGB[1]; shg[3 * (k) + 2] += w_ * dRGB[2]; } \
+        else { shg[3 * (k)] = w_ * dRGB[0]; shg[3 * (k) + 1] = w_ * dRGB[1]; shg[3 * (k) + 2] = w_ * dRGB[2]; } }
         const float xx = dx * dx, yy = dy * dy, zz = dz * dz, xy = dx * dy, yz = dy * dz, xz = dx * dz;
-        // (1) gradient w.r.t. the view direction: reads the SH row, so it runs BEFORE the row is overwritten in place
+        // (1) gradient w.r.t. the view direction (reads the SH row)
         if (deg > 0) {
 #pragma unroll
             for (int ch = 0; ch < 3; ch++) {
@@ -240,7 +298,7 @@ surfel_bwd_body(const CamParams& c, const int idx, const int M, float* osh, cons
                 ddx += gx * dRGB[ch]; ddy += gy * dRGB[ch]; ddz += gz * dRGB[ch];
             }
         }
-        // (2) dL/dSH, written over the row
+        // (2) dL/dSH into the gradient row (summed over frames when the SH tensor is shared by the batch)
         SETSH(0, kSH_C0);
         if (deg > 0) {
             SETSH(1, -kSH_C1 * dy); SETSH(2, kSH_C1 * dz); SETSH(3, -kSH_C1 * dx);
@@ -257,7 +315,7 @@ surfel_bwd_body(const CamParams& c, const int idx, const int M, float* osh, cons
         }
         // coefficients above the active degree receive no gradient
         const int used = (deg + 1) * (deg + 1);
-        for (int k = used; k < M; k++) { osh[3 * k] = 0.f; osh[3 * k + 1] = 0.f; osh[3 * k + 2] = 0.f; }
+        if (!ACC) for (int k = used; k < M; k++) { shg[3 * k] = 0.f; shg[3 * k + 1] = 0.f; shg[3 * k + 2] = 0.f; }
 #undef SH
 #undef SETSH
         // through the normalisation of the view direction (auxiliary.h:125-135)
@@ -267,22 +325,20 @@ surfel_bwd_body(const CamParams& c, const int idx, const int M, float* osh, cons
         dmean[1] += (-dox * doy * ddx + (sum2 - doy * doy) * ddy - doz * doy * ddz) * inv32;
         dmean[2] += (-dox * doz * ddx - doy * doz * ddy + (sum2 - doz * doz) * ddz) * inv32;
     }
-    dL_dmeans3D[3 * (size_t)idx] = dmean[0];
-    dL_dmeans3D[3 * (size_t)idx + 1] = dmean[1];
-    dL_dmeans3D[3 * (size_t)idx + 2] = dmean[2];
+    G.m3d[0] = dmean[0]; G.m3d[1] = dmean[1]; G.m3d[2] = dmean[2];
 }
 
 }  // namespace
 
 cudaError_t launch_surfel_bwd(const BwdArgs& a) {
     const int nb = (a.cam.P + SB - 1) / SB;
-    const size_t smem = (size_t)SB * (3 * a.cam.M + 1) * sizeof(float);
+    const size_t smem = (size_t)2 * SB * (3 * a.cam.M + 1) * sizeof(float);
     if (smem > 48 * 1024) {   // per device context; cheap, not a stream operation
         cudaError_t e = cudaFuncSetAttribute(surfel_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
     ProfileScope ps("surfel_bwd", a.stream);
-    surfel_bwd_kernel<<<dim3(nb, a.fs.frames), SB, smem, a.stream>>>(
+    surfel_bwd_kernel<<<nb, SB, smem, a.stream>>>(
         a.cam, a.fs, a.means3D, a.shs, (const float2*)a.scales, (const float4*)a.rotations, a.radii,
         (const float4*)(a.geom + a.gl.surfel_rec), (const uint8_t*)(a.geom + a.gl.clamped),
         (const float4*)(a.geom + a.gl.sgrad), a.dL_dmeans2D, a.dL_dcolors, a.dL_dopacity, a.dL_dmeans3D,

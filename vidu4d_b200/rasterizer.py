@@ -308,7 +308,7 @@ class _CNamespace:
         means3D, sh, colors, opacity, scales, rotations = (ins[k] for k in ("means3D", "sh", "colors", "opacity", "scales", "rotations"))
         P = int(means3D.shape[-2])
         Msh = int(sh.shape[-2]) if sh is not None and sh.numel() != 0 else 0
-        bt = _capi.SrBatch(M, strides["means3D"], strides["sh"], strides["colors"], strides["opacity"], strides["scales"],
+        bt = _capi.SrBatch(M, 0, strides["means3D"], strides["sh"], strides["colors"], strides["opacity"], strides["scales"],
                            strides["rotations"])
         with torch.cuda.device(dev):
             out_color = torch.empty((M, 3, H, W), dtype=torch.float32, device=dev)
@@ -353,10 +353,17 @@ class _CNamespace:
     @staticmethod
     def rasterize_gaussians_backward_batch(background, means3D, radii, colors, scales, rotations, scale_modifier, viewmatrix,
                                            projmatrix, tan_fovx, tan_fovy, dL_dout_color, dL_dout_others, sh, degree, campos,
-                                           geomBuffer, binningBuffer, imageBuffer, grad_scale=None, debug=False):
+                                           geomBuffer, binningBuffer, imageBuffer, grad_scale=None, debug=False,
+                                           sum_shared=False, opacity_shared=True, want_transmat=True, outs=None):
         """Backward of rasterize_gaussians_batch.  dL_dout_color (M,3,H,W), dL_dout_others (M,8,H,W); grad_scale: optional
-        0-d device tensor multiplying both (the upstream scalar of a fused loss).  Returns the eight gradient tensors, each
-        with a leading M: (M,P,.)."""
+        0-d device tensor multiplying both (the upstream scalar of a fused loss).  Returns the eight gradient tensors
+        (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dtransMat, dL_dsh, dL_dscales, dL_drotations), each with a
+        leading M: (M,P,.).  With sum_shared=True the gradients of inputs the frames SHARE come back summed over the frames
+        with the input's own shape (P,.) -- the per-surfel kernel accumulates them in place, nothing (M,P,.)-sized is
+        written or reduced; `opacity_shared` says whether the forward's opacities were shared (they are not an input of
+        the backward); dL_dmeans2D stays (M,P,3); want_transmat=False skips the (M,P,9) by-product.
+        outs: optional {"dL_dmeans3D" | "dL_dsh" | "dL_dopacity" | "dL_dscales" | "dL_drotations" | "dL_dcolors": tensor}
+        of pre-allocated, suitably shaped and aligned outputs (e.g. views of the flat buffer an all-reduce runs over)."""
         lib = _capi.load()
         M = int(viewmatrix.shape[0])
         dev = means3D.device
@@ -369,13 +376,28 @@ class _CNamespace:
         means3D, sh, colors, scales, rotations = (ins[k] for k in ("means3D", "sh", "colors", "scales", "rotations"))
         P = int(means3D.shape[-2])
         Msh = int(sh.shape[-2]) if sh is not None and sh.numel() != 0 else 0
-        bt = _capi.SrBatch(M, strides["means3D"], strides["sh"], strides["colors"], 0, strides["scales"], strides["rotations"])
+        op_stride = 0 if (opacity_shared or M == 1) else P
+        bt = _capi.SrBatch(M, _capi.SR_BATCH_SUM_SHARED if sum_shared else 0, strides["means3D"], strides["sh"], strides["colors"],
+                           op_stride, strides["scales"], strides["rotations"])
         with torch.cuda.device(dev):
-            mk = (lambda *s: torch.empty(s, dtype=torch.float32, device=dev)) if P > 0 else \
-                 (lambda *s: torch.zeros(s, dtype=torch.float32, device=dev))
-            dL_dmeans3D, dL_dmeans2D, dL_dcolors = mk(M, P, 3), mk(M, P, 3), mk(M, P, 3)
-            dL_dopacity, dL_dtransMat, dL_dsh = mk(M, P, 1), mk(M, P, 9), mk(M, P, Msh, 3)
-            dL_dscales, dL_drotations = mk(M, P, 2), mk(M, P, 4)
+            mk0 = (lambda *s: torch.empty(s, dtype=torch.float32, device=dev)) if P > 0 else \
+                  (lambda *s: torch.zeros(s, dtype=torch.float32, device=dev))
+
+            def mk(name, shared, *tail):   # (M,P,.) per frame, or (P,.) when the input is shared and the kernel sums over frames
+                shape = (P,) + tail if (sum_shared and shared and M > 1) else (M, P) + tail
+                o = outs.get(name) if outs else None
+                if o is not None:
+                    if (o.numel() != int(torch.Size(shape).numel()) or not o.is_contiguous() or o.dtype != torch.float32
+                            or o.data_ptr() % 16 != 0):
+                        raise RuntimeError(f"outs[{name!r}] must be a contiguous, 16-byte aligned float32 tensor of {shape}")
+                    return o.view(shape)
+                return mk0(*shape)
+            dL_dmeans2D = mk0(M, P, 3)
+            dL_dmeans3D, dL_dcolors = mk("dL_dmeans3D", strides["means3D"] == 0, 3), mk("dL_dcolors", strides["colors"] == 0, 3)
+            dL_dopacity = mk("dL_dopacity", op_stride == 0, 1)
+            dL_dtransMat = mk0(M, P, 9) if (want_transmat or (M == 1 and not sum_shared)) else None
+            dL_dsh = mk("dL_dsh", strides["sh"] == 0, Msh, 3)
+            dL_dscales, dL_drotations = mk("dL_dscales", strides["scales"] == 0, 2), mk("dL_drotations", strides["rotations"] == 0, 4)
             if P > 0:
                 cap = _capacity_from_bytes(int(binningBuffer.numel()) // M, W, H)
                 fr = _capi.SrFrame(P, int(degree), Msh, W, H, _as_float(tan_fovx), _as_float(tan_fovy),
@@ -389,8 +411,8 @@ class _CNamespace:
                     _ptr(dL_dout_color), _ptr(dL_dout_others), gs.data_ptr() if gs is not None else None,
                     geomBuffer.data_ptr(), binningBuffer.data_ptr(), imageBuffer.data_ptr(), cap,
                     dL_dmeans2D.data_ptr(), dL_dcolors.data_ptr(), dL_dopacity.data_ptr(), dL_dmeans3D.data_ptr(),
-                    dL_dtransMat.data_ptr(), dL_dsh.data_ptr() if Msh > 0 else None, dL_dscales.data_ptr(),
-                    dL_drotations.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+                    dL_dtransMat.data_ptr() if dL_dtransMat is not None else None, dL_dsh.data_ptr() if Msh > 0 else None,
+                    dL_dscales.data_ptr(), dL_drotations.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
                 _capi.check(rc, "sr_backward_batch")
         return dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dtransMat, dL_dsh, dL_dscales, dL_drotations
 
@@ -508,7 +530,9 @@ def _reduce_like(grad, inp):
     """(M,P,.) per-frame gradient -> the input's shape: inputs shared by all frames get the sum over frames."""
     if inp is None or inp.numel() == 0:
         return None
-    return grad if inp.ndim == grad.ndim else grad.sum(dim=0).view(inp.shape)
+    if grad.ndim == inp.ndim:                 # per-frame input, or already summed over the frames by the kernel
+        return grad.view(inp.shape)
+    return grad.sum(dim=0).view(inp.shape)
 
 
 class _RasterizeGaussiansBatch(torch.autograd.Function):
@@ -538,7 +562,7 @@ class _RasterizeGaussiansBatch(torch.autograd.Function):
         g2d, gcol, gop, g3d, gtm, gsh, gsc, grot = _C.rasterize_gaussians_backward_batch(
             rs.bg, means3D, radii, colors_precomp, scales, rotations, rs.scale_modifier, rs.viewmatrix, rs.projmatrix,
             rs.tanfovx, rs.tanfovy, grad_color, grad_allmap, sh, rs.sh_degree, rs.campos, geomBuffer, binningBuffer, imgBuffer,
-            None, rs.debug)
+            None, rs.debug, sum_shared=True, opacity_shared=opacities.ndim == 2, want_transmat=False)
         return (_reduce_like(g3d, means3D), g2d, _reduce_like(gsh, sh), _reduce_like(gcol, colors_precomp),
                 _reduce_like(gop, opacities), _reduce_like(gsc, scales), _reduce_like(grot, rotations), None)
 

@@ -371,7 +371,7 @@ class _RasterLossBatch(torch.autograd.Function):
         from . import _capi
         from .rasterizer import _C
         lib = _capi.load()
-        cams, bg, sh_degree, target, vis, mask, mask_wt, depth_ratio, w_rgb, w_mask, lam_n, lam_d, tanx, tany = cfg
+        cams, bg, sh_degree, target, vis, mask, mask_wt, depth_ratio, w_rgb, w_mask, lam_n, lam_d, tanx, tany, target_stream = cfg
         M, H, W = len(cams), cams.image_height, cams.image_width
         dev = means3D.device
         e = torch.empty((0,), dtype=torch.float32, device=dev)
@@ -387,6 +387,8 @@ class _RasterLossBatch(torch.autograd.Function):
         f32 = lambda t: None if t is None else t.to(dtype=torch.float32).contiguous()  # noqa: E731
         target, vis, mask, mask_wt = f32(target), f32(vis), f32(mask), f32(mask_wt)
         bk = f32(bkgd.detach()) if bkgd is not None else None
+        if target_stream is not None:       # the targets are still being uploaded on another stream: join it only now,
+            torch.cuda.current_stream(dev).wait_stream(target_stream)   # after the rasterizer forward has been queued
         with torch.cuda.device(dev):
             rc = lib.sr_render_loss_batch(M, W, H, tanx, tany, float(depth_ratio), color.data_ptr(), allmap.data_ptr(),
                                           cams.world_view_transform.data_ptr(), target.data_ptr(), ptr(vis), ptr(mask), ptr(mask_wt),
@@ -410,14 +412,15 @@ class _RasterLossBatch(torch.autograd.Function):
         e = torch.empty((0,), dtype=torch.float32, device=means3D.device)
         g2d, gcol, gop, g3d, gtm, gsh, gsc, grot = _C.rasterize_gaussians_backward_batch(
             bg, means3D, radii, e, scales, rotations, 1.0, cams.world_view_transform, cams.full_proj_transform, tanx, tany,
-            dLc, dLa, sh, sh_degree, cams.camera_center, gb, bb, ib, grad_scale=g_total)
+            dLc, dLa, sh, sh_degree, cams.camera_center, gb, bb, ib, grad_scale=g_total, sum_shared=True,
+            opacity_shared=opacities.ndim == 2, want_transmat=False)
         g_bk = (dLb.sum(0) * g_total) if ctx.has_bkgd else None
         return (_reduce_like(g3d, means3D), g2d, _reduce_like(gsh, sh), _reduce_like(gop, opacities),
                 _reduce_like(gsc, scales), _reduce_like(grot, rotations), g_bk, None)
 
 
 def render_loss_batch(cameras, pc, pipe, bg_color, target_rgb, vis2d=None, mask_gt=None, mask_wt=None, learnable_bkgd=None,
-                      w_rgb=1.0, w_mask=0.0, lambda_normal=0.0, lambda_dist=0.0, means3D=None, rotations=None):
+                      w_rgb=1.0, w_mask=0.0, lambda_normal=0.0, lambda_dist=0.0, means3D=None, rotations=None, target_stream=None):
     """The Stage-3 inner loop for M frames in one call: rasterize every frame (batched launch set), post-process and
     evaluate the image losses in one fused kernel, and hand autograd a single scalar.
 
@@ -425,6 +428,8 @@ def render_loss_batch(cameras, pc, pipe, bg_color, target_rgb, vis2d=None, mask_
     optional per-frame overrides -- the bob-warped surfels of each frame (DeformableGaussian._override_xyz/_rotation,
     lab4d/nnutils/deformable_gaussian.py:163-176); default = pc.get_xyz / pc.get_rotation shared by all frames.
     target_rgb (M,3,H,W); vis2d / mask_gt / mask_wt (M,H,W) or None; learnable_bkgd (3,) or None.
+    target_stream: CUDA stream on which target_rgb (and the masks) are still being produced, e.g. an H2D copy running
+    beside the rasterizer forward; it is joined right before the loss kernel (None: the tensors are ready).
 
     Returns {"loss": scalar (sum over frames and terms, differentiable), "terms": (M,4) weighted rgb/mask/normal/dist
     (detached), "render": (M,3,H,W), "allmap": (M,8,H,W), "radii": (M,P), "visibility_filter": (M,P),
@@ -438,7 +443,7 @@ def render_loss_batch(cameras, pc, pipe, bg_color, target_rgb, vis2d=None, mask_
     screenspace_points = torch.zeros((M, P, 3), dtype=xyz.dtype, requires_grad=True, device=xyz.device)
     tanx, tany = _cam_tans(cameras)
     cfg = (cameras, bg_color, pc.active_sh_degree, target_rgb, vis2d, mask_gt, mask_wt, float(pipe.depth_ratio),
-           w_rgb, w_mask, lambda_normal, lambda_dist, tanx, tany)
+           w_rgb, w_mask, lambda_normal, lambda_dist, tanx, tany, target_stream)
     total, terms, color, allmap, radii = _RasterLossBatch.apply(xyz, screenspace_points, pc.get_features, pc.get_opacity,
                                                                 pc.get_scaling, rot, learnable_bkgd, cfg)
     return {"loss": total, "terms": terms, "render": color, "allmap": allmap, "radii": radii,

@@ -225,6 +225,31 @@ SR_API int sr_render_loss_batch(int32_t M, int32_t W, int32_t H, float tan_fovx,
                                 float* loss_terms, float* dL_dcolor, float* dL_dallmap, float* dL_dbkgd,
                                 float* surf_depth_scratch, void* stream);
 
+/*
+ * Fused bob-skinning warp: canonical surfels -> every frame's camera space.
+ * Replaces the PyTorch chain of lab4d/nnutils/deformable_gaussian.py:1395-1434 (forward_warp), :1033-1046
+ * (apply_qt_to_gaussian), lab4d/nnutils/warping.py:378-444 (SkinningWarp.forward, forward direction),
+ * lab4d/nnutils/skinning.py:89-142 (Gaussian skinning logits), lab4d/utils/geom_utils.py:48-92 (sign-aligned
+ * dual-quaternion blend) and the quaternion helper kernels of lab4d/third_party/quaternion/src/quaternion.cu.
+ *   xyz[P*3], rot[P*4] (w,x,y,z): canonical surfels;  o2b_q[B*4], o2b_t[B*3]: object->bone transform of the rest pose;
+ *   inv_gauss[B*3] = exp(-log_gauss);  delta[P*B] or NULL;  se3_r, se3_d[M*B*4]: per frame and bone dual quaternion
+ *   t_articulation o rest_articulation^-1;  cam_q[M*4], cam_t[M*3]: field2cam.   B <= 64.
+ * forward writes xyz_cam[M*P*3], rot_cam[M*P*4] (feed them to sr_forward_batch with per-frame strides) and
+ * skin_entropy[P] (may be NULL).  backward takes their gradients (g_entropy may be NULL) and writes g_xyz[P*3], g_rot[P*4],
+ * g_delta[P*B] (if non-NULL) and g_tables[sr_bob_warp_table_floats(B, M)] = gradients of {o2b_q, o2b_t, inv_gauss, se3_r,
+ * se3_d, cam_q, cam_t} in that order (zeroed inside).
+ */
+SR_API size_t sr_bob_warp_table_floats(int32_t B, int32_t M);
+SR_API int sr_bob_warp_forward(int32_t P, int32_t B, int32_t M, const float* xyz, const float* rot, const float* o2b_q,
+                               const float* o2b_t, const float* inv_gauss, const float* delta, const float* se3_r,
+                               const float* se3_d, const float* cam_q, const float* cam_t, float* xyz_cam, float* rot_cam,
+                               float* skin_entropy, void* stream);
+SR_API int sr_bob_warp_backward(int32_t P, int32_t B, int32_t M, const float* xyz, const float* rot, const float* o2b_q,
+                                const float* o2b_t, const float* inv_gauss, const float* delta, const float* se3_r,
+                                const float* se3_d, const float* cam_q, const float* cam_t, const float* g_xyz_cam,
+                                const float* g_rot_cam, const float* g_entropy, float* g_xyz, float* g_rot, float* g_delta,
+                                float* g_tables, void* stream);
+
 SR_API int sr_abi_version(void);
 SR_API const char* sr_last_error(void);
 /* number of kernel launches issued by this library since load (bench.py's `gpu_launches`) */

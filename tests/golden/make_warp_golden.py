@@ -1,7 +1,11 @@
 """Generate tests/golden/warp_*.npz from the REFERENCE's own warp code, run on the CPU in this container.
 
-Nothing is copied: at run time this script loads lab4d/utils/quat_transform.py from /root/reference by path (its compiled
-`quaternion` CUDA helper module is stubbed -- on CPU tensors the file uses its own pure-torch `_quaternion_mul`), and
+Nothing is copied: at run time this script loads lab4d/utils/quat_transform.py from /root/reference by path.  Its compiled
+`quaternion` CUDA helper (lab4d/third_party/quaternion) cannot be built here, and the file's own CPU branch only handles
+4-vectors, while the warp multiplies 3-vectors (zero real part) with quaternions -- something only the CUDA helper does
+(quaternion.cu:40-57: a 3-component operand gets w = 0).  quaternion_mul / quaternion_conjugate are therefore re-pointed
+to a dispatcher over the file's OWN pure-torch kernels `_quaternion_mul`, `_quaternion_4D_mul_3D`, `_quaternion_3D_mul_4D`
+and `_quaternion_conjugate` (same semantics as the CUDA helper).  The script then
 exec()s the source text of get_bone_coords (lab4d/utils/transforms.py), dual_quaternion_skinning (lab4d/utils/geom_utils.py),
 cross_entropy_skin_loss (lab4d/utils/loss_utils.py) and DeformableGaussian.apply_qt_to_gaussian
 (lab4d/nnutils/deformable_gaussian.py) on seeded inputs, chaining them exactly as SkinningWarp.forward
@@ -32,6 +36,17 @@ def _load_reference():
     spec = importlib.util.spec_from_file_location("ref_quat_transform", os.path.join(REF, "lab4d/utils/quat_transform.py"))
     qt = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(qt)
+
+    def qmul(a, b):                      # the CUDA helper's semantics (quaternion.cu:40-57) over the file's own torch kernels
+        shape = torch.broadcast_shapes(a.shape[:-1], b.shape[:-1])
+        a = a.expand(shape + a.shape[-1:]); b = b.expand(shape + b.shape[-1:])
+        if a.shape[-1] == 3 and b.shape[-1] == 4:
+            return qt._quaternion_3D_mul_4D(a, b)
+        if a.shape[-1] == 4 and b.shape[-1] == 3:
+            return qt._quaternion_4D_mul_3D(a, b)
+        return qt._quaternion_mul(a, b)
+    qt.quaternion_mul = qmul
+    qt.quaternion_conjugate = qt._quaternion_conjugate
     ns = {k: getattr(qt, k) for k in dir(qt) if not k.startswith("__")}
     ns.update(torch=torch, F=F)
 

@@ -19,7 +19,7 @@ SR_BATCH_SUM_SHARED = 1
 SYMBOLS = (
     "sr_geom_bytes", "sr_image_bytes", "sr_binning_bytes", "sr_forward", "sr_backward",
     "sr_mark_visible", "sr_debug_view", "sr_abi_version", "sr_last_error", "sr_launch_count",
-    "sr_set_profiling", "sr_get_profile", "sr_post_forward", "sr_post_backward", "sr_forward_batch", "sr_backward_batch", "sr_render_loss_batch",
+    "sr_set_profiling", "sr_get_profile", "sr_post_forward", "sr_post_backward", "sr_forward_batch", "sr_backward_batch", "sr_render_loss_batch", "sr_bob_warp_table_floats", "sr_bob_warp_forward", "sr_bob_warp_backward",
 )
 
 
@@ -96,6 +96,12 @@ def load():
     lib.sr_post_backward.argtypes = [i32, i32, C.c_float, C.c_float, C.c_float] + [vp] * 12
     lib.sr_render_loss_batch.restype = C.c_int
     lib.sr_render_loss_batch.argtypes = [i32, i32, i32, C.c_float, C.c_float, C.c_float] + [vp] * 8 + [C.c_float] * 4 + [vp] * 6
+    lib.sr_bob_warp_table_floats.restype = C.c_size_t
+    lib.sr_bob_warp_table_floats.argtypes = [i32, i32]
+    lib.sr_bob_warp_forward.restype = C.c_int
+    lib.sr_bob_warp_forward.argtypes = [i32, i32, i32] + [vp] * 14
+    lib.sr_bob_warp_backward.restype = C.c_int
+    lib.sr_bob_warp_backward.argtypes = [i32, i32, i32] + [vp] * 18
     lib.sr_set_profiling.restype = None
     lib.sr_set_profiling.argtypes = [C.c_int]
     lib.sr_get_profile.restype = C.c_char_p

@@ -61,8 +61,12 @@ __device__ __forceinline__ void get_rect(float px, float py, int max_radius, int
     rmax.y = min((unsigned)gy, (unsigned)max(0, y1));
 }
 
-// forward.cu:20-71 (value-level parity only; no binning decision depends on the colour)
-__device__ __forceinline__ float3 sh_to_rgb(int deg, int M, float3 pos, const float* __restrict__ campos,
+// forward.cu:20-71.  No binning decision depends on the colour, so this is not written with explicit-rounding
+// intrinsics; it mirrors the reference's expression tree and lets nvcc contract it -- which reproduces the reference
+// build's bits ONLY while the compiler sees the function in isolation: inlined into the batched kernel, 9 more
+// multiply-adds were fused and 0.1 % of the pixels moved by one ulp (r2b).  Hence __noinline__: the call costs nothing
+// next to the 48 coefficient loads, and the colour planes stay bit-identical to the reference (tests assert it).
+__device__ __noinline__ float3 sh_to_rgb(int deg, int M, float3 pos, const float* __restrict__ campos,
                                             const float* sh, uint32_t& clamped) {
     float dx = pos.x - __ldg(campos), dy = pos.y - __ldg(campos + 1), dz = pos.z - __ldg(campos + 2);
     float len = sqrtf(dx * dx + dy * dy + dz * dz);

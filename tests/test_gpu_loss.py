@@ -54,7 +54,7 @@ def test_render_loss_batch_matches_oracle(with_bkgd, depth_ratio, dev):
                             means3D=cloud.get_xyz[None] + shift, **kw)
     (out["loss"] * 1.7).backward()                    # a non-unit upstream scalar exercises grad_scale
     got = [p.grad.detach().cpu().numpy() for p in cloud.flat_params()]
-    assert out["terms"].shape == (M, 4) and abs(float(out["terms"].sum()) - float(out["loss"])) <= 1e-5 * abs(float(out["loss"]))
+    assert out["terms"].shape == (M, 4) and abs(float(out["terms"].sum()) - float(out["loss"].detach())) <= 1e-5 * abs(float(out["loss"].detach()))
 
     # ---- oracle: per frame, losses on the rasterizer's planes; VJP pushed through the single-frame rasterizer backward
     cloud2 = SurfelCloud(scene, dev)

@@ -250,6 +250,19 @@ SR_API int sr_bob_warp_backward(int32_t P, int32_t B, int32_t M, const float* xy
                                 const float* g_rot_cam, const float* g_entropy, float* g_xyz, float* g_rot, float* g_delta,
                                 float* g_tables, void* stream);
 
+/*
+ * Optimizer-side kernels over the FLAT surfel parameter buffer: the Adam step of every
+ * surfel parameter group in one launch (lab4d/engine/trainer.py:243-253,585-586; torch.optim.Adam semantics), and
+ * densify / prune as one gather into new buffers (gs/scene/gaussian_model.py:291-446).  See csrc/optim.cu.
+ */
+SR_API int sr_adam_flat(int32_t n_groups, const int64_t* begin, const float* lr, float beta1, float beta2, float eps,
+                        int64_t step, float grad_scale, float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                        void* stream);
+SR_API int sr_surfel_compact(int32_t n_groups, const int32_t* width, const int64_t* old_begin, const int64_t* new_begin,
+                             int32_t xyz_group, int32_t scaling_group, int32_t P_new, const int32_t* src, const uint8_t* kind,
+                             const int32_t* child_slot, const float* child_xyz, const float* child_scaling, const float* p_old,
+                             const float* m_old, const float* v_old, float* p_new, float* m_new, float* v_new, void* stream);
+
 SR_API int sr_abi_version(void);
 SR_API const char* sr_last_error(void);
 /* number of kernel launches issued by this library since load (bench.py's `gpu_launches`) */

@@ -34,6 +34,9 @@ def test_render_loss_batch_matches_oracle(with_bkgd, depth_ratio, dev):
         R, t = orbit_view(5 * f + 2, 64)
         cams.append(make_camera(W, H, 2 * np.arctan(tanx), 2 * np.arctan(tany), R=R.T, T=t, device=dev))
     bc = stack_cameras(cams)
+    # hand the matrices in as a STRIDED view (as bench.py does: one (M,2,4,4) upload holding view and projection matrices)
+    both = torch.stack((bc.world_view_transform, bc.full_proj_transform), 1)
+    bc.world_view_transform, bc.full_proj_transform = both[:, 0], both[:, 1]
     scene = object_scene(P, seed=21, center=(0.0, 0.0, 0.0))
     gen = torch.Generator(device=dev).manual_seed(7)
     target = torch.rand((M, 3, H, W), device=dev, generator=gen)

@@ -62,6 +62,8 @@ def parse():
     ap.add_argument("--mode", default="batch", choices=["batch", "streams"], help="ours: one batched launch set per step, or F single-frame calls over --streams CUDA streams")
     ap.add_argument("--no-value-graph", action="store_true", help="keep the value-arm step eager (no CUDA-graph capture)")
     ap.add_argument("--no-variants", action="store_true", help="skip the 1- and 2-frame-per-call variants of the value arm")
+    ap.add_argument("--split", type=int, default=1, help="batch mode: render the step's frames as this many sub-batches on parallel "
+                    "streams inside the captured step (bandwidth-bound kernels of one overlap the composites of another)")
     ap.add_argument("--no-ref-cuda", action="store_true", help="skip timing the reference extension in the ours arm")
     ap.add_argument("--ref-device", default="cuda", choices=["cuda", "cpu"])
     ap.add_argument("--no-graph", action="store_true", help="keep the e2e step eager (no CUDA-graph capture)")
@@ -224,7 +226,7 @@ def main():
     # alternating over `--streams` CUDA streams, per-stream gradient rows reduced once per step.
     BATCH = args.impl == "ours" and args.mode == "batch"
     NS = 1 if (args.impl != "ours" or BATCH) else max(1, args.streams)
-    side = [torch.cuda.Stream(device=device) for _ in range(max(NS, 2))]
+    side = [torch.cuda.Stream(device=device) for _ in range(max(NS, 2, args.split))]
     nflt = acc_flat_bytes // 4
     stack = torch.zeros((NS, nflt), device=device)
     flat_acc = torch.zeros((nflt,), device=device) if (NS > 1 or BATCH) else stack[0]
@@ -245,12 +247,34 @@ def main():
     value_graph = [None]
     R_last_box = [0]
 
+    SPLIT = max(1, args.split) if BATCH else 1
+    split_rows = torch.zeros((SPLIT, nflt), device=device) if SPLIT > 1 else None
+    split_outs = [dict(zip(("dL_dmeans3D", "dL_dsh", "dL_dopacity", "dL_dscales", "dL_drotations"), views(split_rows[k])))
+                  for k in range(SPLIT)] if SPLIT > 1 else None
+
     def batch_body(fpc=None):
         """One batched forward+backward of `fpc` frames (default F) + the sum over frames into the flat gradient."""
         n = F if fpc is None else fpc
         idx = (step_ctr * (world * F) + rank * F + ar[:n]) % NVIEWS
         step_ctr.add_(1)
         vm_b, pm_b, cp_b = vms.index_select(0, idx), pms.index_select(0, idx), cps.index_select(0, idx)
+        if SPLIT > 1 and n == F:
+            main = torch.cuda.current_stream()
+            sub = F // SPLIT
+            o = None
+            for k in range(SPLIT):
+                side[k].wait_stream(main)
+                with torch.cuda.stream(side[k]):
+                    sl = slice(k * sub, (k + 1) * sub)
+                    o = C.rasterize_gaussians_batch(bg, t_in["means3D"], e, t_in["opac"], t_in["scales"], t_in["rots"], 1.0, vm_b[sl],
+                                                    pm_b[sl], TAN, TAN, RES, RES, t_in["shs"], 3, cp_b[sl])
+                    C.rasterize_gaussians_backward_batch(bg, t_in["means3D"], o[3], e, t_in["scales"], t_in["rots"], 1.0, vm_b[sl],
+                                                         pm_b[sl], TAN, TAN, dLc_b[sl], dLo_b[sl], t_in["shs"], 3, cp_b[sl], o[4], o[5],
+                                                         o[6], sum_shared=True, want_transmat=False, outs=split_outs[k])
+            for k in range(SPLIT):
+                main.wait_stream(side[k])
+            torch.sum(split_rows, dim=0, out=flat_acc)
+            return o
         o = C.rasterize_gaussians_batch(bg, t_in["means3D"], e, t_in["opac"], t_in["scales"], t_in["rots"], 1.0, vm_b, pm_b,
                                         TAN, TAN, RES, RES, t_in["shs"], 3, cp_b)
         # gradients of the (shared) surfel parameters are summed over the frames inside the per-surfel kernel and land
@@ -689,7 +713,7 @@ def main():
                        "surfels": P, "resolution": RES, "frames_per_step_per_gpu": F, "instances_per_frame": R_inst,
                        "parallelism": f"frames sharded over {world} GPU(s), 1 NCCL all-reduce of {acc_flat_bytes >> 20} MiB/step" if world > 1 else "1 GPU",
                        "streams": NS, "mode": (args.mode if args.impl == "ours" else "reference: single-frame calls, legacy default stream"),
-                       "value_step": value_mode,
+                       "value_step": value_mode, "split": (max(1, args.split) if args.impl == "ours" and args.mode == "batch" else None),
                        "l2": f"explicit flush (256 MiB write) between timed steps; per-step working set also exceeds the {L2_MB} MB L2"},
             "e2e": {"value": round(e2e_value, 2), "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
                     "mode": e2e_mode, "check_vs_eager": e2e_check, "api": "render_loss_batch" if BATCH else ("render_fused" if render is render_fused else "render"),

@@ -8,6 +8,9 @@ backward -> Adam -- on a synthetic 32-frame sequence, 300 K surfels, 256x256, M 
               (oracle/_ref/_C.so through render()) frame by frame + torch losses
   ours        the same PyTorch warp + render_loss_batch (batched B200 rasterizer, fused post-processing + losses)
   ours_fused  fused warp kernel (csrc/warp.cu) + render_loss_batch
+  ours_graph  ours_fused with the WHOLE step (bone tables -> warp -> rasterize -> losses -> backward -> Adam) captured in a
+              CUDA graph (vidu4d_b200.graph.GraphedStep): the step is ~25 kernels of this library plus ~100 tiny torch
+              kernels for the B x M bone tables, so eager launch overhead is most of what is left
 
 It reports steps/s of each and the warp's share of a step (CUDA events around the warp's forward and backward), which is
 the number that says whether SURVEY.md 8(f) row N2 pays.
@@ -121,7 +124,53 @@ class WarpedView:
     get_features = property(lambda s: s._c.get_features)
 
 
+def run_graph(surfels, res, frames, steps, bones, warm=5, seed=0):
+    """ours_fused, whole step in one CUDA graph.  The frame pair of a step is a device tensor the graph reads."""
+    from vidu4d_b200.graph import GraphedStep
+    dev = torch.device("cuda:0")
+    M = 2
+    cloud = SurfelCloud(object_scene(surfels, seed=seed, center=(0.0, 0.0, 0.0)), dev)
+    seq = Sequence(bones, frames, 0.35, dev, seed)
+    tan = 0.5
+    fov = 2 * math.atan(tan)
+    eye = torch.eye(4, device=dev)[None].expand(M, -1, -1).contiguous()
+    pm = torch.from_numpy(projection_matrix(tan, tan)).to(dev)[None].expand(M, -1, -1).contiguous()
+    bc = BatchCameras(res, res, fov, fov, eye, pm, torch.zeros((M, 3), device=dev))
+    bg = torch.zeros(3, device=dev)
+    pipe = PipelineParams()
+    targets = torch.rand((frames, 3, res, res), generator=torch.Generator().manual_seed(1)).to(dev)
+    params = cloud.flat_params() + list(seq.parameters())
+    opt = torch.optim.Adam(params, lr=1e-5, fused=True, capturable=True)
+    fr = torch.zeros((M,), dtype=torch.int64, device=dev)
+    loss_out = torch.zeros((), device=dev)
+
+    def body():
+        opt.zero_grad(set_to_none=False)
+        rest, art, lg, f2c = seq.tables(fr)
+        xc, rc, ent = bob_warp(cloud.get_xyz, cloud._rotation, rest, art, lg, f2c)
+        loss = render_loss_batch(bc, cloud, pipe, bg, targets.index_select(0, fr), w_rgb=1.0, lambda_normal=0.05, lambda_dist=0.01,
+                                 means3D=xc, rotations=torch.nn.functional.normalize(rc, dim=-1))["loss"]
+        loss.backward()
+        opt.step()
+        loss_out.copy_(loss.detach())
+        fr.add_(2).remainder_(frames)
+    fr.copy_(torch.tensor([0, 1], device=dev))
+    step = GraphedStep(body, device=dev)
+    t0 = None
+    for i in range(steps + warm):
+        if i == warm:
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+        step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    RZ.set_sync_mode(True); RZ._pending.clear()
+    return {"backend": "ours_graph", "steps_per_s": round(steps / dt, 2), "frames_per_s": round(M * steps / dt, 2),
+            "ms_per_step": round(dt / steps * 1e3, 3), "loss": float(loss_out), "graph_launches_of_this_library": step.launches}
+
+
 def run(backend, surfels, res, frames, steps, bones, warm=5, seed=0):
+    if backend == "ours_graph":
+        return run_graph(surfels, res, frames, steps, bones, warm, seed)
     dev = torch.device("cuda:0")
     M = 2
     cloud = SurfelCloud(object_scene(surfels, seed=seed, center=(0.0, 0.0, 0.0)), dev)
@@ -198,7 +247,7 @@ if __name__ == "__main__":
     ap.add_argument("--frames", type=int, default=32)
     ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--bones", type=int, default=25)
-    ap.add_argument("--backends", default="ours_fused,ours,reference")
+    ap.add_argument("--backends", default="ours_graph,ours_fused,ours,reference")
     a = ap.parse_args()
     out = {"config": f"C3: {a.surfels} surfels, {a.frames}-frame sequence, {a.res}x{a.res}, M=2 frames/step, B={a.bones} bones, 1 GPU", "results": []}
     for b in a.backends.split(","):

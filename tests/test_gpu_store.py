@@ -177,7 +177,7 @@ def test_graphed_step_recaptures_on_growth_and_on_overflow(dev):
         assert step.captures == 2 and m.grad_flat.numel() == m.flat.numel()
         # (b) the scene grows inside the same P: inflate the surfels so that num_rendered exceeds the baked capacity
         with torch.no_grad():
-            m._scaling += 1.6
+            m._scaling += 3.0
         step()                                       # overflow detected -> hints refreshed -> re-captured -> re-run
         assert step.captures == 3
         eager = render_fused(cam, m, PipelineParams(), bg)["render"].detach().clone()

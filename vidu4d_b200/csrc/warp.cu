@@ -176,6 +176,24 @@ bob_warp_fwd_kernel(const WarpDims d, const float* __restrict__ xyz, const float
     }
 }
 
+// Recursive-halving warp reduction of 32 values: lane L ends with the sum over the warp of v[L].  31 shuffles for 32
+// sums (a plain shuffle tree needs 5 per value) and the 32 results land one per lane, so the shared-memory accumulation
+// that follows is ONE conflict-free atomic instruction instead of 32 single-lane ones.
+__device__ __forceinline__ float butterfly32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int off = 16, n = 16; off >= 1; off >>= 1, n >>= 1) {
+        const bool hi = lane & off;
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            if (i < n) {
+                const float keep = hi ? v[i + n] : v[i], send = hi ? v[i] : v[i + n];
+                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            }
+        }
+    }
+    return v[0];
+}
+
 // warp sum, then one shared-memory add per warp (only the 8 warps of a block contend on an address)
 __device__ __forceinline__ void acc_table(float* slot, float v) {
 #pragma unroll
@@ -255,15 +273,28 @@ bob_warp_bwd_kernel(const WarpDims d, const float* __restrict__ xyz, const float
         const float* sr = T.sr + (size_t)m * B * 4;
         const float* sd = T.sd + (size_t)m * B * 4;
         const Q4 qa = ldq(sr + 4 * anchor);
+        const int lane = threadIdx.x & 31;
 #pragma unroll
-        for (int b = 0; b < BMAX; b++) {
-            if (b < B) {
-                const Q4 rb = ldq(sr + 4 * b), db = ldq(sd + 4 * b);
-                const float s = qdot(qa, rb) > 0.f ? 1.f : -1.f;
-                gw[b] += s * (qdot(gQR, rb) + qdot(gQD, db));
-                const float ws = w[b] * s;
-                acc_q(g_sr + ((size_t)m * B + b) * 4, qscale(gQR, ws));
-                acc_q(g_sd + ((size_t)m * B + b) * 4, qscale(gQD, ws));
+        for (int c4 = 0; c4 < BMAX / 4; c4++) {
+            if (4 * c4 < B) {                                        // four bones x (4 + 4) components = 32 sums per butterfly
+                float vals[32];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int b = 4 * c4 + j;
+                    float ws = 0.f;
+                    if (b < B) {
+                        const Q4 rb = ldq(sr + 4 * b), db = ldq(sd + 4 * b);
+                        const float s = qdot(qa, rb) > 0.f ? 1.f : -1.f;
+                        gw[b] += s * (qdot(gQR, rb) + qdot(gQD, db));
+                        ws = w[b] * s;
+                    }
+                    vals[8 * j] = gQR.w * ws; vals[8 * j + 1] = gQR.x * ws; vals[8 * j + 2] = gQR.y * ws; vals[8 * j + 3] = gQR.z * ws;
+                    vals[8 * j + 4] = gQD.w * ws; vals[8 * j + 5] = gQD.x * ws; vals[8 * j + 6] = gQD.y * ws; vals[8 * j + 7] = gQD.z * ws;
+                }
+                const float tot = butterfly32(vals, lane);
+                const int b = 4 * c4 + (lane >> 3), comp = lane & 7;
+                if (b < B && tot != 0.f)
+                    atomicAdd((comp < 4 ? g_sr : g_sd) + ((size_t)m * B + b) * 4 + (comp & 3), tot);
             }
         }
     }
@@ -272,25 +303,42 @@ bob_warp_bwd_kernel(const WarpDims d, const float* __restrict__ xyz, const float
 #pragma unroll
     for (int b = 0; b < BMAX; b++) dotwg += w[b] * gw[b];
     const float ge = (g_entropy && live) ? g_entropy[ps] : 0.f;
+    const int lane = threadIdx.x & 31;
 #pragma unroll
-    for (int b = 0; b < BMAX; b++) {
-        if (b < B) {
-            const float gl = (w[b] * (gw[b] - dotwg) + ge * (w[b] - (b == anchor ? 1.f : 0.f))) * lv;
-            if (g_delta && live) g_delta[ps * B + b] = -gl;
-            const Q4 qb = ldq(T.oq + 4 * b);
-            float bx, by, bz;
-            qrot(qb, x, y, z, bx, by, bz);
-            bx += T.ot[3 * b]; by += T.ot[3 * b + 1]; bz += T.ot[3 * b + 2];
-            const float i0 = T.ig[3 * b], i1 = T.ig[3 * b + 1], i2 = T.ig[3 * b + 2];
-            // logit = -(|xb * ig|^2 + delta):  g_s = -2 s gl
-            const float gs0 = -2.f * bx * i0 * gl, gs1 = -2.f * by * i1 * gl, gs2 = -2.f * bz * i2 * gl;
-            acc_table(g_ig + 3 * b, gs0 * bx); acc_table(g_ig + 3 * b + 1, gs1 * by); acc_table(g_ig + 3 * b + 2, gs2 * bz);
-            const float gb0 = gs0 * i0, gb1 = gs1 * i1, gb2 = gs2 * i2;
-            acc_table(g_ot + 3 * b, gb0); acc_table(g_ot + 3 * b + 1, gb1); acc_table(g_ot + 3 * b + 2, gb2);
-            Q4 gqb; float ax, ay, az;
-            qrot_vjp(qb, x, y, z, gb0, gb1, gb2, gqb, ax, ay, az);
-            acc_q(g_oq + 4 * b, gqb);
-            gxx += ax; gxy += ay; gxz += az;
+    for (int c3 = 0; c3 < (BMAX + 2) / 3; c3++) {
+        if (3 * c3 < B) {                                            // three bones x (4 + 3 + 3) components per butterfly
+            float vals[32];
+            vals[30] = 0.f; vals[31] = 0.f;
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                const int b = 3 * c3 + j;
+#pragma unroll
+                for (int i = 0; i < 10; i++) vals[10 * j + i] = 0.f;
+                if (b < B && b < BMAX) {
+                    const float gl = (w[b] * (gw[b] - dotwg) + ge * (w[b] - (b == anchor ? 1.f : 0.f))) * lv;
+                    if (g_delta && live) g_delta[ps * B + b] = -gl;
+                    const Q4 qb = ldq(T.oq + 4 * b);
+                    float bx, by, bz;
+                    qrot(qb, x, y, z, bx, by, bz);
+                    bx += T.ot[3 * b]; by += T.ot[3 * b + 1]; bz += T.ot[3 * b + 2];
+                    const float i0 = T.ig[3 * b], i1 = T.ig[3 * b + 1], i2 = T.ig[3 * b + 2];
+                    // logit = -(|xb * ig|^2 + delta):  g_s = -2 s gl
+                    const float gs0 = -2.f * bx * i0 * gl, gs1 = -2.f * by * i1 * gl, gs2 = -2.f * bz * i2 * gl;
+                    const float gb0 = gs0 * i0, gb1 = gs1 * i1, gb2 = gs2 * i2;
+                    Q4 gqb; float ax, ay, az;
+                    qrot_vjp(qb, x, y, z, gb0, gb1, gb2, gqb, ax, ay, az);
+                    gxx += ax; gxy += ay; gxz += az;
+                    vals[10 * j] = gqb.w; vals[10 * j + 1] = gqb.x; vals[10 * j + 2] = gqb.y; vals[10 * j + 3] = gqb.z;
+                    vals[10 * j + 4] = gb0; vals[10 * j + 5] = gb1; vals[10 * j + 6] = gb2;
+                    vals[10 * j + 7] = gs0 * bx; vals[10 * j + 8] = gs1 * by; vals[10 * j + 9] = gs2 * bz;
+                }
+            }
+            const float tot = butterfly32(vals, lane);
+            const int j = lane / 10, i = lane - 10 * j, b = 3 * c3 + j;
+            if (lane < 30 && b < B && tot != 0.f) {
+                float* dst = i < 4 ? g_oq + 4 * b + i : (i < 7 ? g_ot + 3 * b + (i - 4) : g_ig + 3 * b + (i - 7));
+                atomicAdd(dst, tot);
+            }
         }
     }
     if (live) {
@@ -356,7 +404,8 @@ SR_API int sr_bob_warp_backward(int32_t P, int32_t B, int32_t M, const float* xy
     ProfileScope ps("bob_warp_bwd", s);
     auto launch = [&](auto kern) -> int {
         if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return SR_ECUDA;
-        kern<<<(P + 255) / 256, 256, smem, s>>>(d, xyz, rot, o2b_q, o2b_t, inv_gauss, delta, se3_r, se3_d, cam_q, cam_t, g_xyz_cam,
+        // 128-thread blocks: the kernel holds ~200 registers per thread (B weights + B weight gradients)
+        kern<<<(P + 127) / 128, 128, smem, s>>>(d, xyz, rot, o2b_q, o2b_t, inv_gauss, delta, se3_r, se3_d, cam_q, cam_t, g_xyz_cam,
                                                  g_rot_cam, g_entropy, g_xyz, g_rot, g_delta, g_tables);
         return 0;
     };

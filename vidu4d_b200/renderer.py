@@ -387,11 +387,12 @@ class _RasterLossBatch(torch.autograd.Function):
         f32 = lambda t: None if t is None else t.to(dtype=torch.float32).contiguous()  # noqa: E731
         target, vis, mask, mask_wt = f32(target), f32(vis), f32(mask), f32(mask_wt)
         bk = f32(bkgd.detach()) if bkgd is not None else None
+        wvt = f32(cams.world_view_transform)         # (M,4,4) packed: callers may hand in a strided view
         if target_stream is not None:       # the targets are still being uploaded on another stream: join it only now,
             torch.cuda.current_stream(dev).wait_stream(target_stream)   # after the rasterizer forward has been queued
         with torch.cuda.device(dev):
             rc = lib.sr_render_loss_batch(M, W, H, tanx, tany, float(depth_ratio), color.data_ptr(), allmap.data_ptr(),
-                                          cams.world_view_transform.data_ptr(), target.data_ptr(), ptr(vis), ptr(mask), ptr(mask_wt),
+                                          wvt.data_ptr(), target.data_ptr(), ptr(vis), ptr(mask), ptr(mask_wt),
                                           ptr(bk), float(w_rgb), float(w_mask), float(lam_n), float(lam_d), terms.data_ptr(),
                                           dLc.data_ptr(), dLa.data_ptr(), ptr(dLb), scratch.data_ptr(),
                                           torch.cuda.current_stream(dev).cuda_stream)

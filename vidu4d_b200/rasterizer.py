@@ -111,8 +111,21 @@ def check_overflow(keep: bool = False):
     replay: call check_overflow(keep=True) after each replay)."""
     global _host_next
     bad, prefilter = None, False
+    # Every device a pending forward ran on is synchronised (not just the current one): the asynchronous D2H copies of the
+    # status words have landed.  Device-wide rather than per stream, because a forward recorded into a CUDA graph replays
+    # on whatever stream the graph is launched on, not on the stream it was captured on.
+    devices, bare = set(), []
+    for _, _, _, stream in _pending:
+        d = getattr(stream, "device", None)
+        if d is not None:
+            devices.add(d)
+        elif stream not in bare:
+            bare.append(stream)
+    for d in devices:
+        torch.cuda.synchronize(d)
+    for stream in bare:
+        stream.synchronize()
     for host, key, cap, stream in _pending:
-        stream.synchronize()          # the stream (and device) the forward ran on: its D2H copy of the words has landed
         for r, status in host.tolist():
             _cap_hint[key] = max(_cap_hint.get(key, 0), r)
             if status & _capi.SR_STATUS_OVERFLOW:

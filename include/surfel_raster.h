@@ -263,6 +263,15 @@ SR_API int sr_surfel_compact(int32_t n_groups, const int32_t* width, const int64
                              const int32_t* child_slot, const float* child_xyz, const float* child_scaling, const float* p_old,
                              const float* m_old, const float* v_old, float* p_new, float* m_new, float* v_new, void* stream);
 
+/*
+ * Mean squared distance of every point to its 3 nearest neighbours: `distCUDA2` of gs/submodules/simple-knn
+ * (simple_knn.cu:132-218), used once to initialise the surfel scales (gs/scene/gaussian_model.py:139-140).
+ * sr_knn_cells() gives the grid size for a bounding box (host floats); scratch = device int32[2*P + 3*cells].
+ */
+SR_API int64_t sr_knn_cells(int32_t P, const float* bbox_min, const float* bbox_max, float* h_out, int32_t* dims_out);
+SR_API int sr_knn_mean_dist2(int32_t P, const float* points, const float* bbox_min, const float* bbox_max, float* out,
+                             int32_t* scratch, void* stream);
+
 SR_API int sr_abi_version(void);
 SR_API const char* sr_last_error(void);
 /* number of kernel launches issued by this library since load (bench.py's `gpu_launches`) */

@@ -187,3 +187,28 @@ def test_graphed_step_recaptures_on_growth_and_on_overflow(dev):
     finally:
         RZ.set_sync_mode(True)
         RZ._pending.clear()
+
+
+@pytest.mark.parametrize("P,kind", [(20000, "sphere"), (5000, "blob"), (4, "tiny"), (3000, "dups")])
+def test_knn_mean_dist2_matches_brute_force(P, kind, dev):
+    """distCUDA2 (simple_knn.cu:132-218): exact 3-NN mean squared distance, duplicates included, against brute force."""
+    from vidu4d_b200.knn import distCUDA2
+    g = torch.Generator(device=dev).manual_seed(P)
+    if kind == "sphere":
+        x = torch.randn((P, 3), device=dev, generator=g); x = x / x.norm(dim=1, keepdim=True) * 0.35
+    elif kind == "dups":
+        x = torch.randn((P // 3, 3), device=dev, generator=g).repeat(3, 1)
+    else:
+        x = torch.randn((P, 3), device=dev, generator=g) * torch.tensor([1.0, 0.2, 3.0], device=dev)
+    got = distCUDA2(x)
+    want = torch.empty_like(got)
+    xd = x.double()
+    for s in range(0, x.shape[0], 2000):
+        d = torch.cdist(xd[s:s + 2000], xd).pow(2)
+        d[torch.arange(d.shape[0]), torch.arange(s, s + d.shape[0])] = float("inf")
+        k = min(3, x.shape[0] - 1)
+        best = torch.topk(d, k, dim=1, largest=False).values
+        if k < 3:                         # fewer than 3 other points: the reference leaves FLT_MAX in the unused slots
+            best = torch.cat([best, torch.full((best.shape[0], 3 - k), 3.4e38, dtype=torch.float64, device=dev)], 1)
+        want[s:s + d.shape[0]] = (best.sum(1) / 3).float()
+    assert float(((got - want).abs() / (want.abs() + 1e-12)).max()) <= 1e-4

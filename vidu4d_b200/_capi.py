@@ -19,7 +19,7 @@ SR_BATCH_SUM_SHARED = 1
 SYMBOLS = (
     "sr_geom_bytes", "sr_image_bytes", "sr_binning_bytes", "sr_forward", "sr_backward",
     "sr_mark_visible", "sr_debug_view", "sr_abi_version", "sr_last_error", "sr_launch_count",
-    "sr_set_profiling", "sr_get_profile", "sr_post_forward", "sr_post_backward", "sr_forward_batch", "sr_backward_batch", "sr_render_loss_batch", "sr_bob_warp_table_floats", "sr_bob_warp_forward", "sr_bob_warp_backward", "sr_adam_flat", "sr_surfel_compact",
+    "sr_set_profiling", "sr_get_profile", "sr_post_forward", "sr_post_backward", "sr_forward_batch", "sr_backward_batch", "sr_render_loss_batch", "sr_bob_warp_table_floats", "sr_bob_warp_forward", "sr_bob_warp_backward", "sr_adam_flat", "sr_surfel_compact", "sr_knn_cells", "sr_knn_mean_dist2",
 )
 
 
@@ -106,6 +106,10 @@ def load():
     lib.sr_adam_flat.argtypes = [i32, vp, vp, C.c_float, C.c_float, C.c_float, i64, C.c_float, vp, vp, vp, vp, vp]
     lib.sr_surfel_compact.restype = C.c_int
     lib.sr_surfel_compact.argtypes = [i32, vp, vp, vp, i32, i32, i32] + [vp] * 12
+    lib.sr_knn_cells.restype = C.c_int64
+    lib.sr_knn_cells.argtypes = [i32, vp, vp, vp, vp]
+    lib.sr_knn_mean_dist2.restype = C.c_int
+    lib.sr_knn_mean_dist2.argtypes = [i32, vp, vp, vp, vp, vp, vp]
     lib.sr_set_profiling.restype = None
     lib.sr_set_profiling.argtypes = [C.c_int]
     lib.sr_get_profile.restype = C.c_char_p

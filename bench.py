@@ -287,16 +287,37 @@ def main():
                 a_.add_(gr[gi].reshape(a_.shape))
         return o
 
+    # Two captures of the same step, used alternately, each with its own pinned status words and a "done" event: the host
+    # checks step k-1's overflow words only AFTER it has queued step k, so the GPU never waits for the host between steps
+    # (and the ranks of a multi-GPU run do not drift apart at the collective).  The check is still once per step.
+    done_ev = [torch.cuda.Event(), torch.cuda.Event()]
+    inflight = [None]
+
+    def drain():
+        """Wait for the step still in flight (if any) and check its overflow words."""
+        if inflight[0] is not None:
+            k = inflight[0]
+            done_ev[k].synchronize()
+            arm(value_graphs[k])
+            RZ.check_overflow(keep=True, sync=False)
+            inflight[0] = None
+
     def step_dev(step):
         R_last = 0
         if BATCH:
             if value_graph[0] is not None:
-                value_graph[0].replay()
-            else:
-                batch_body()
+                k = step & 1
+                value_graphs[k].replay()
+                if world > 1:
+                    torch.distributed.all_reduce(flat_acc)
+                done_ev[k].record()
+                drain()                     # step k-1 (the other graph): its words landed long ago
+                inflight[0] = k
+                return R_last
+            batch_body()
             if world > 1:
                 torch.distributed.all_reduce(flat_acc)
-            RZ.check_overflow(keep=value_graph[0] is not None)     # the step's only host<->device synchronisation
+            RZ.check_overflow()             # eager fallback: the step's only host<->device synchronisation
             return R_last
         main = torch.cuda.current_stream()
         if NS > 1:
@@ -359,13 +380,18 @@ def main():
         RZ._pending[:] = gph.watch if gph is not None else []
 
     value_mode = "eager"
+    value_graphs = [None, None]
     if BATCH and not args.no_value_graph:
-        value_graph[0] = capture(batch_body, "the value-arm step")
-        value_mode = "cuda_graph(batched forward+backward+frame-sum)" if value_graph[0] is not None else "eager (capture failed)"
+        value_graphs = [capture(batch_body, "the value-arm step"), capture(batch_body, "the value-arm step (second copy)")]
+        value_graph[0] = value_graphs[0] if all(g is not None for g in value_graphs) else None
+        value_mode = ("2 x cuda_graph(batched forward+backward+frame-sum), overflow check of step k-1 after step k is queued"
+                      if value_graph[0] is not None else "eager (capture failed)")
 
     def timed(step_fn, nsteps, nwarm):
         for s in range(nwarm):
             step_fn(s)
+        if step_fn is step_dev and BATCH:
+            drain()
         sync_all(world)
         starts = [torch.cuda.Event(enable_timing=True) for _ in range(nsteps)]
         ends = [torch.cuda.Event(enable_timing=True) for _ in range(nsteps)]
@@ -375,6 +401,8 @@ def main():
             starts[s].record()
             step_fn(nwarm + s)
             ends[s].record()
+        if step_fn is step_dev and BATCH:
+            drain()                                   # the last step's overflow check (inside the wall-clock, after its event)
         sync_all(world)
         wall = (time.perf_counter() - t0) * 1e3
         per = [a.elapsed_time(b) for a, b in zip(starts, ends)]

@@ -104,11 +104,12 @@ def _host_slot(frames: int = 1):
     return h[:frames]
 
 
-def check_overflow(keep: bool = False):
+def check_overflow(keep: bool = False, sync: bool = True):
     """nosync mode: synchronise once, verify that no forward since the last call overflowed its instance
     buffer, and refresh the capacity hints.  Raises SurfelRasterError if a frame was dropped.
     keep=True leaves the watch list in place (a captured CUDA graph rewrites the same status words on every
-    replay: call check_overflow(keep=True) after each replay)."""
+    replay: call check_overflow(keep=True) after each replay).  sync=False: the caller has already waited for the
+    forwards in question (e.g. on an event recorded behind them) -- used to check step k-1 while step k is in flight."""
     global _host_next
     bad, prefilter = None, False
     # Every device a pending forward ran on is synchronised (not just the current one): the asynchronous D2H copies of the
@@ -121,10 +122,11 @@ def check_overflow(keep: bool = False):
             devices.add(d)
         elif stream not in bare:
             bare.append(stream)
-    for d in devices:
-        torch.cuda.synchronize(d)
-    for stream in bare:
-        stream.synchronize()
+    if sync:
+        for d in devices:
+            torch.cuda.synchronize(d)
+        for stream in bare:
+            stream.synchronize()
     for host, key, cap, stream in _pending:
         for r, status in host.tolist():
             _cap_hint[key] = max(_cap_hint.get(key, 0), r)

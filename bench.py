@@ -686,14 +686,20 @@ def main():
             ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(dom, {})
         except Exception:
             pass
+        # the capture is of a batch of `frames_per_launch` frames per launch: rescale to this run's launch
+        nfl = float(ncu.get("frames_per_launch", 1) or 1)
         traffic = ncu.get("dram_bytes_per_launch")
+        if traffic is not None:
+            traffic = int(traffic * Fl / nfl)
         frame_alg = 1002 * P + 324 * R_inst + 128 * N
         roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                     "frac": round(ach / hbm_peak, 5), "traffic": traffic, "peak_source": peak_src,
                     "alg_bytes_per_launch": alg.get(dom, 0) * Fl, "impl_bytes_per_launch": impl.get(dom, alg.get(dom, 0)) * Fl,
                     "launch_ms": kernels[dom]["ms_per_launch"], "frames_per_launch": Fl,
-                    "traffic_note": "dram bytes of ONE frame's launch from profiles/ncu_traffic.json (ncu --set full)",
-                    "l2_red_sectors": ncu.get("l2_red_sectors"), "lanes_active": ncu.get("lanes_active"),
+                    "traffic_note": "dram__bytes_read+write of this kernel's launch from the committed ncu --set full capture "
+                                    "(profiles/ncu_traffic.json), rescaled to this run's frames per launch",
+                    "l2_red_sectors": (None if ncu.get("l2_red_sectors") is None else int(ncu["l2_red_sectors"] * Fl / nfl)),
+                    "lanes_active": ncu.get("lanes_active"),
                     "contributing_pairs": pairs_contrib, "visible_surfels": Vv,
                     "note": "the composite kernels are FP32-issue / latency bound by construction (SURVEY 8d): each instance record "
                             "is read once per tile but evaluated against ~10 pixels; algorithmic HBM bytes are small. "

@@ -72,6 +72,11 @@ def main():
             open(fn, "w").write(f"# ncu --set full --clock-control none  ({tag})\n" + txt + "\n")
     if outdir:
         json.dump(counters, open(os.path.join(outdir, f"ncu_counters_{tag}.json"), "w"), indent=1)
+        if len(sys.argv) > 3:      # frames per launch of the captured command: also refresh profiles/ncu_traffic.json for bench.py
+            fpl = int(sys.argv[3])
+            alias = {"onesweep_pass": "onesweep_passes"}
+            traffic = {alias.get(k, k): dict(v, frames_per_launch=fpl, capture=tag) for k, v in counters.items()}
+            json.dump(traffic, open(os.path.join(outdir, "ncu_traffic.json"), "w"), indent=1)
 
 if __name__ == "__main__":
     main()

@@ -226,3 +226,57 @@ def test_check_overflow_bookkeeping_without_a_gpu(built, monkeypatch):
             R.check_overflow()
     finally:
         R._pending[:] = saved[0]; R._cap_hint.clear(); R._cap_hint.update(saved[1]); R._host_next = saved[2]
+
+
+def test_batch_descriptor_and_validation_without_gpu(built):
+    """The batched entry points validate their descriptor before any CUDA call; sr_batch's ctypes layout matches the C one."""
+    from vidu4d_b200 import _capi
+    lib = _capi.load()
+    assert C.sizeof(_capi.SrBatch) == 8 + 6 * 8                      # int32 frames, uint32 flags, six int64 strides
+    fr = _capi.SrFrame(10, 3, 16, 64, 64, 0.5, 0.5, 1.0, 0, 0, 0)
+    nul = [None] * 16 + [0] + [None] * 3
+    for frames in (0, -3, 70000):
+        bt = _capi.SrBatch(frames, 0, 0, 0, 0, 0, 0, 0)
+        assert lib.sr_forward_batch(C.byref(fr), C.byref(bt), *nul) == -1 and b"frames" in lib.sr_last_error()
+    assert lib.sr_forward_batch(C.byref(fr), None, *nul) == -1
+    bt = _capi.SrBatch(2, 0, 0, 0, 0, 0, 0, 0)
+    nulb = [None] * 13 + [None, None, None, 0] + [None] * 9
+    assert lib.sr_backward_batch(C.byref(fr), C.byref(bt), *nulb) == -1 and b"NULL" in lib.sr_last_error()
+    # pure host helpers
+    assert lib.sr_bob_warp_table_floats(25, 2) == 25 * 10 + 2 * 25 * 8 + 2 * 7
+    assert lib.sr_bob_warp_forward(10, 65, 1, *([None] * 14)) == -1                 # more than 64 bones
+    assert lib.sr_adam_flat(0, None, None, 0.9, 0.999, 1e-15, 1, 1.0, None, None, None, None, None) == -1
+    lo, hi = (C.c_float * 3)(0, 0, 0), (C.c_float * 3)(1, 2, 0.5)
+    h, dims = C.c_float(), (C.c_int32 * 3)()
+    cells = lib.sr_knn_cells(10000, lo, hi, C.byref(h), dims)
+    assert cells == dims[0] * dims[1] * dims[2] and 1000 < cells < 100000 and 0.02 < h.value < 0.2
+
+
+def test_batch_input_normalisation_on_cpu():
+    """_batch_inputs: shared (single-frame shape) vs per-frame (leading M) inputs -> strides in floats; shape errors."""
+    from vidu4d_b200 import rasterizer as R
+
+    class _T:            # _f32c insists on CUDA tensors: stand-in with the attributes _batch_inputs reads
+        pass
+    orig = R._f32c
+    R._f32c = lambda t, name: t
+    try:
+        ins, st = R._batch_inputs(3, means3D=(torch.zeros(3, 10, 3), (3,)), sh=(torch.zeros(10, 16, 3), None),
+                                  rotations=(torch.zeros(10, 4), (4,)), colors=(torch.zeros(0), (3,)))
+        assert st == {"means3D": 30, "sh": 0, "rotations": 0, "colors": 0} and ins["colors"] is None
+        with pytest.raises(RuntimeError, match="leading dimension"):
+            R._batch_inputs(3, means3D=(torch.zeros(2, 10, 3), (3,)))
+        with pytest.raises(RuntimeError, match="trailing dimensions"):
+            R._batch_inputs(3, scales=(torch.zeros(10, 3), (2,)))
+        with pytest.raises(RuntimeError, match="dimensions"):
+            R._batch_inputs(3, means3D=(torch.zeros(3), (3,)))
+    finally:
+        R._f32c = orig
+    assert R.BatchRasterizationSettings._fields[:10] == R.GaussianRasterizationSettings._fields[:10]
+
+
+def test_flat_surfel_layout_matches_flatgrads_order():
+    """The flat store's group order and widths are the gs_optimizer's (lab4d/engine/trainer.py:243-251) and FlatGrads'."""
+    from vidu4d_b200.surfel_store import GROUPS
+    assert [n for n, _ in GROUPS] == ["xyz", "f_dc", "f_rest", "opacity", "scaling", "rotation"]
+    assert sum(k for _, k in GROUPS) == 58

@@ -22,7 +22,7 @@ namespace {
 using namespace comp;
 
 template <int G, int ABL = 0>
-__global__ void __launch_bounds__(32 * WPC, 32 / WPC)
+__global__ void __launch_bounds__(32 * WPC)
 composite_fwd_kernel(const FrameStrides fs, const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order, int n_items, int tiles_x,
                      const float4* __restrict__ irec, int W, int H,
                      const float* __restrict__ bg, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,

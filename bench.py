@@ -663,11 +663,11 @@ def main():
         # ALGORITHMIC bytes per frame of each kernel (split per kernel in DESIGN.md section 3);
         # implementation-only traffic (contribution masks, instance-record stream written by the gather) is listed apart
         alg = {
-            "preprocess_fwd": P * (40 + 12 * 16) + Vv * 87 + (P // 256) * 8,
-            "emit_keys": P * 20 + R_inst * 12, "sort_histogram": R_inst * 8 + 6 * 256 * 8,
-            "onesweep_passes": R_inst * 24 * 6, "ranges_gather": R_inst * 8 + 20 * (RES // 16) ** 2,
+            "preprocess_fwd": P * (40 + 12 * 16) + Vv * 87, "scan_block_sums": (P // 256) * 8,
+            "emit_keys": P * 20 + R_inst * 12, "sort_histogram": R_inst * 8, "sort_plan": 6 * 256 * 8,
+            "onesweep_passes": R_inst * 24 * 6, "ranges_gather": R_inst * 8 + 8 * (RES // 16) ** 2,
             "composite_fwd": R_inst * 76 + N * 64, "composite_bwd": R_inst * 76 + N * 64 + Vv * 72,
-            "surfel_bwd": Vv * (343 + 240),
+            "surfel_bwd": Vv * (343 + 240), "tile_order": 12 * (RES // 16) ** 2,
         }
         impl = {"ranges_gather": R_inst * (12 + 80 + 80), "composite_fwd": R_inst * (80 + 32) + N * 64,
                 "composite_bwd": R_inst * (80 + 32) + N * 64 + Vv * 80}

@@ -8,6 +8,8 @@ backward -> Adam -- on a synthetic 32-frame sequence, 300 K surfels, 256x256, M 
               (oracle/_ref/_C.so through render()) frame by frame + torch losses
   ours        the same PyTorch warp + render_loss_batch (batched B200 rasterizer, fused post-processing + losses)
   ours_fused  fused warp kernel (csrc/warp.cu) + render_loss_batch
+  ours_full   ours_graph + FlatSurfelModel: flat parameter buffer, one-kernel Adam, densification statistics in the captured step
+              (`ours_full_densify`: one densify_and_prune + graph re-capture in the middle of the timed loop)
   ours_graph  ours_fused with the WHOLE step (bone tables -> warp -> rasterize -> losses -> backward -> Adam) captured in a
               CUDA graph (vidu4d_b200.graph.GraphedStep): the step is ~25 kernels of this library plus ~100 tiny torch
               kernels for the B x M bone tables, so eager launch overhead is most of what is left
@@ -168,9 +170,73 @@ def run_graph(surfels, res, frames, steps, bones, warm=5, seed=0):
             "ms_per_step": round(dt / steps * 1e3, 3), "loss": float(loss_out), "graph_launches_of_this_library": step.launches}
 
 
+def run_full(surfels, res, frames, steps, bones, warm=5, seed=0, densify_at=None):
+    """Everything on the fast path: FlatSurfelModel (flat parameter buffer, one-kernel Adam, one-gather densify / prune),
+    fused warp, render_loss_batch, the step as one CUDA graph that is re-captured when densification changes P."""
+    from vidu4d_b200.graph import GraphedStep
+    from vidu4d_b200.surfel_store import FlatSurfelModel
+    dev = torch.device("cuda:0")
+    M = 2
+    sc = object_scene(surfels, seed=seed, center=(0.0, 0.0, 0.0))
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    op = np.clip(sc.opacities, 1e-6, 1 - 1e-6)
+    model = FlatSurfelModel(t(sc.means3D), t(sc.shs[:, :1]), t(sc.shs[:, 1:]), t(np.log(op / (1 - op))), t(np.log(sc.scales)), t(sc.rotations),
+                            lrs={"xyz": 1e-5, "f_dc": 1e-5, "f_rest": 1e-5, "opacity": 1e-5, "scaling": 1e-5, "rotation": 1e-5})
+    seq = Sequence(bones, frames, 0.35, dev, seed)
+    tan = 0.5
+    fov = 2 * math.atan(tan)
+    eye = torch.eye(4, device=dev)[None].expand(M, -1, -1).contiguous()
+    pm = torch.from_numpy(projection_matrix(tan, tan)).to(dev)[None].expand(M, -1, -1).contiguous()
+    bc = BatchCameras(res, res, fov, fov, eye, pm, torch.zeros((M, 3), device=dev))
+    bg = torch.zeros(3, device=dev)
+    pipe = PipelineParams()
+    targets = torch.rand((frames, 3, res, res), generator=torch.Generator().manual_seed(1)).to(dev)
+    opt = torch.optim.Adam(list(seq.parameters()), lr=1e-5, fused=True, capturable=True)
+    fr = torch.zeros((M,), dtype=torch.int64, device=dev)
+    loss_out = torch.zeros((), device=dev)
+    stats = {}
+
+    def body():
+        opt.zero_grad(set_to_none=False)
+        model.zero_grad_flat()
+        rest, art, lg, f2c = seq.tables(fr)
+        xc, rc, ent = bob_warp(model.get_xyz, model._rotation, rest, art, lg, f2c)
+        out = render_loss_batch(bc, model, pipe, bg, targets.index_select(0, fr), w_rgb=1.0, lambda_normal=0.05, lambda_dist=0.01,
+                                means3D=xc, rotations=torch.nn.functional.normalize(rc, dim=-1))
+        out["loss"].backward()
+        # densification statistics (trainer.py:553-560), inside the graph: per frame, on device
+        for m in range(M):
+            model.add_densification_stats(out["viewspace_points"].grad[m], out["visibility_filter"][m], out["radii"][m])
+        model.adam_step()
+        opt.step()
+        loss_out.copy_(out["loss"].detach())
+        fr.add_(2).remainder_(frames)
+    fr.copy_(torch.tensor([0, 1], device=dev))
+    step = GraphedStep(body, key=lambda: model.P, device=dev)
+    t0 = None
+    for i in range(steps + warm):
+        if i == warm:
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+        if densify_at is not None and i == warm + densify_at:
+            stats = model.densify_and_prune(2e-4, 0.005, 1.0, None)      # P changes: the next step() re-captures
+        step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    RZ.set_sync_mode(True); RZ._pending.clear()
+    return {"backend": "ours_full", "steps_per_s": round(steps / dt, 2), "frames_per_s": round(M * steps / dt, 2),
+            "ms_per_step": round(dt / steps * 1e3, 3), "loss": float(loss_out), "graph_captures": step.captures, "densify": stats,
+            "note": "flat-buffer Adam + densification statistics inside the captured step" + ("; wall time includes one densify_and_prune + re-capture" if densify_at is not None else "")}
+
+
 def run(backend, surfels, res, frames, steps, bones, warm=5, seed=0):
     if backend == "ours_graph":
         return run_graph(surfels, res, frames, steps, bones, warm, seed)
+    if backend == "ours_full":
+        return run_full(surfels, res, frames, steps, bones, warm, seed)
+    if backend == "ours_full_densify":
+        r = run_full(surfels, res, frames, steps, bones, warm, seed, densify_at=steps // 2)
+        r["backend"] = "ours_full_densify"
+        return r
     dev = torch.device("cuda:0")
     M = 2
     cloud = SurfelCloud(object_scene(surfels, seed=seed, center=(0.0, 0.0, 0.0)), dev)
@@ -247,7 +313,7 @@ if __name__ == "__main__":
     ap.add_argument("--frames", type=int, default=32)
     ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--bones", type=int, default=25)
-    ap.add_argument("--backends", default="ours_graph,ours_fused,ours,reference")
+    ap.add_argument("--backends", default="ours_full,ours_graph,ours_fused,ours,reference")
     a = ap.parse_args()
     out = {"config": f"C3: {a.surfels} surfels, {a.frames}-frame sequence, {a.res}x{a.res}, M=2 frames/step, B={a.bones} bones, 1 GPU", "results": []}
     for b in a.backends.split(","):

@@ -202,6 +202,7 @@ int sr_forward_batch(const sr_frame* f, const sr_batch* b, const float* backgrou
     CK(launch_scan_emit(a), "scan/emit_keys"); DBG("scan/emit_keys");
     CK(launch_sort(a), "sort"); DBG("sort");
     CK(launch_ranges_gather(a), "ranges_gather"); DBG("ranges_gather");
+    CK(launch_tile_order(a), "tile_order"); DBG("tile_order");
     if (sr_composite_tile_mode(false)) { CK(launch_composite_tile_fwd(a), "composite_tile_fwd"); }
     else { CK(launch_composite_fwd(a), "composite_fwd"); }
     DBG("composite_fwd");

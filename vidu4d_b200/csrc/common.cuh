@@ -58,9 +58,6 @@
 #define SR_CTL_SKIP 8            // [8 .. 8+MAX_PASSES): 1 = pass is an identity permutation, skipped
 #define SR_CTL_SRC 16            // [16 .. 16+MAX_PASSES): source array (0/1) of pass p
 #define SR_CTL_TILE_COUNTER 24   // [24 .. 24+MAX_PASSES): dynamic tile ids of pass p
-#define SR_CTL_TICKET_PRE 32     // blocks of preprocess_fwd that have published their block sum (last one scans them)
-#define SR_CTL_TICKET_HIST 33    // blocks of sort_histogram done (last one runs the pass plan)
-#define SR_CTL_TICKET_GATHER 34  // blocks of ranges_gather done (last one builds the tile launch order)
 #define SR_CTL_WORDS 64
 
 static inline __host__ __device__ size_t sr_align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
@@ -196,6 +193,7 @@ cudaError_t launch_preprocess_fwd(const FwdArgs& a);      // preprocess.cu
 cudaError_t launch_scan_emit(const FwdArgs& a);           // preprocess.cu
 cudaError_t launch_sort(const FwdArgs& a);                // sort.cu
 cudaError_t launch_ranges_gather(const FwdArgs& a);       // sort.cu
+cudaError_t launch_tile_order(const FwdArgs& a);          // sort.cu
 cudaError_t launch_composite_fwd(const FwdArgs& a);       // composite_fwd.cu
 cudaError_t launch_composite_bwd(const BwdArgs& a);       // composite_bwd.cu
 cudaError_t launch_surfel_bwd(const BwdArgs& a);          // surfel_bwd.cu

@@ -145,15 +145,14 @@ preprocess_fwd_kernel(const CamParams c_, const FrameStrides fs, const float* __
                       const float2* __restrict__ scales, const float4* __restrict__ rotations,
                       int* __restrict__ radii, float4* __restrict__ srec, float* __restrict__ depths,
                       uint32_t* __restrict__ tiles_touched, uint8_t* __restrict__ clamped_out,
-                      uint32_t* __restrict__ block_sums, uint32_t* __restrict__ status, int prefiltered,
-                      uint32_t* __restrict__ ticket, long long capacity) {
+                      uint32_t* __restrict__ block_sums, uint32_t* __restrict__ status, int prefiltered) {
     const int f = blockIdx.y;                       // frame of the batch
     const CamParams c = cam_of_frame(c_, fs, f);
     means3D = fr(means3D, fs.means3D, f); shs = fr(shs, fs.shs, f); colors_precomp = fr(colors_precomp, fs.colors, f);
     opacities = fr(opacities, fs.opac, f); scales = fr(scales, fs.scales, f); rotations = fr(rotations, fs.rots, f);
     radii = fr(radii, fs.radii, f); srec = fr(srec, fs.geom, f); depths = fr(depths, fs.geom, f);
     tiles_touched = fr(tiles_touched, fs.geom, f); clamped_out = fr(clamped_out, fs.geom, f);
-    block_sums = fr(block_sums, fs.geom, f); status = fr(status, fs.nr, f); ticket = fr(ticket, fs.bin, f);
+    block_sums = fr(block_sums, fs.geom, f); status = fr(status, fs.nr, f);
     // The block's SH coefficients (256 x 3M floats, contiguous) are staged in shared memory with coalesced 128-bit
     // loads; each thread then reads its own padded row (stride 3M+1: conflict-free) instead of 48 scalar loads at a
     // 192-byte lane stride.
@@ -270,8 +269,6 @@ preprocess_fwd_kernel(const CamParams c_, const FrameStrides fs, const float* __
     }
     // block sum of tiles_touched -> block_sums[blockIdx.x]
     __shared__ uint32_t wsum[8];
-    __shared__ uint32_t carry_s;
-    __shared__ bool last_s;
     uint32_t v = touched;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -282,39 +279,46 @@ preprocess_fwd_kernel(const CamParams c_, const FrameStrides fs, const float* __
 #pragma unroll
         for (int i = 0; i < 8; i++) tot += wsum[i];
         block_sums[blockIdx.x] = tot;
-        __threadfence();                                   // publish the sum before taking the ticket
-        last_s = atomicAdd(ticket, 1u) == gridDim.x - 1;
-        carry_s = 0;
     }
+}
+
+// exclusive scan of block_sums[0..nb) in place; block_sums[nb] = total; publishes R and the overflow flag
+__global__ void __launch_bounds__(1024)
+scan_block_sums_kernel(const FrameStrides fs, uint32_t* __restrict__ block_sums, int nb, uint32_t* __restrict__ num_rendered,
+                       long long capacity) {
+    block_sums = fr(block_sums, fs.geom, (int)blockIdx.x);          // one block per frame
+    num_rendered = fr(num_rendered, fs.nr, (int)blockIdx.x);
+    __shared__ uint32_t wtot[32];
+    __shared__ uint32_t carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
-    if (!last_s) return;
-    // The LAST block to finish turns the block sums into exclusive offsets (InclusiveSum, rasterizer_impl.cu:278) and
-    // publishes R and the overflow flag -- what used to be a separate single-block kernel (and its launch latency).
-    __threadfence();
-    const int nb = gridDim.x;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int base = 0; base < nb; base += 256) {
+    for (int base = 0; base < nb; base += 1024) {
         const int i = base + threadIdx.x;
-        const uint32_t val = i < nb ? __ldcg(block_sums + i) : 0u;
-        uint32_t inc = val;
+        const uint32_t v = i < nb ? block_sums[i] : 0u;
+        uint32_t inc = v;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const uint32_t n = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += n; }
-        if (lane == 31) wsum[warp] = inc;
+        for (int o = 1; o < 32; o <<= 1) { uint32_t n = __shfl_up_sync(0xffffffffu, inc, o); if ((threadIdx.x & 31) >= o) inc += n; }
+        if ((threadIdx.x & 31) == 31) wtot[threadIdx.x >> 5] = inc;
         __syncthreads();
-        uint32_t wb = 0;
+        if (threadIdx.x < 32) {
+            uint32_t w = wtot[threadIdx.x], winc = w;
 #pragma unroll
-        for (int w = 0; w < 8; w++) wb += w < warp ? wsum[w] : 0u;
-        const uint32_t excl = carry_s + wb + inc - val;
+            for (int o = 1; o < 32; o <<= 1) { uint32_t n = __shfl_up_sync(0xffffffffu, winc, o); if (threadIdx.x >= o) winc += n; }
+            wtot[threadIdx.x] = winc - w;   // exclusive
+        }
+        __syncthreads();
+        const uint32_t carry = carry_s;
+        const uint32_t excl = carry + wtot[threadIdx.x >> 5] + inc - v;
         if (i < nb) block_sums[i] = excl;
         __syncthreads();
-        if (threadIdx.x == 255) carry_s = excl + val;
+        if (threadIdx.x == 1023) carry_s = excl + v;
         __syncthreads();
     }
     if (threadIdx.x == 0) {
         const uint32_t R = carry_s;
         block_sums[nb] = R;
-        status[-1] = R;                                    // status points at num_rendered[1]; [0] is R
-        if ((long long)R > capacity) atomicOr(status, SR_STATUS_OVERFLOW);
+        num_rendered[0] = R;
+        if ((long long)R > capacity) atomicOr(num_rendered + 1, SR_STATUS_OVERFLOW);
     }
 }
 
@@ -403,8 +407,7 @@ cudaError_t launch_preprocess_fwd(const FwdArgs& a) {
         a.cam, a.fs, a.means3D, a.shs, a.colors_precomp, a.opacities, (const float2*)a.scales, (const float4*)a.rotations,
         a.radii, (float4*)(a.geom + a.gl.surfel_rec), (float*)(a.geom + a.gl.depths),
         (uint32_t*)(a.geom + a.gl.tiles_touched), (uint8_t*)(a.geom + a.gl.clamped),
-        (uint32_t*)(a.geom + a.gl.block_sums), a.num_rendered_dev + 1, a.prefiltered,
-        (uint32_t*)(a.bin + a.bl.sort_ctl) + SR_CTL_TICKET_PRE, (long long)a.bl.capacity);
+        (uint32_t*)(a.geom + a.gl.block_sums), a.num_rendered_dev + 1, a.prefiltered);
     sr_count_launch();
     return cudaGetLastError();
 }
@@ -412,12 +415,14 @@ cudaError_t launch_preprocess_fwd(const FwdArgs& a) {
 cudaError_t launch_scan_emit(const FwdArgs& a) {
     const int nb = a.gl.nblocks;
     uint32_t* bs = (uint32_t*)(a.geom + a.gl.block_sums);
+    { ProfileScope ps("scan_block_sums", a.stream);
+      scan_block_sums_kernel<<<a.fs.frames, 1024, 0, a.stream>>>(a.fs, bs, nb, a.num_rendered_dev, (long long)a.bl.capacity); }
     ProfileScope ps("emit_keys", a.stream);
     emit_keys_kernel<<<dim3(nb, a.fs.frames), 256, 0, a.stream>>>(
         a.cam, a.fs, (const float4*)(a.geom + a.gl.surfel_rec), (const float*)(a.geom + a.gl.depths), a.radii,
         (const uint32_t*)(a.geom + a.gl.tiles_touched), bs, (uint32_t*)(a.geom + a.gl.point_offsets),
         (uint64_t*)(a.bin + a.bl.keys[0]), (uint32_t*)(a.bin + a.bl.values[0]), (long long)a.bl.capacity);
-    sr_count_launch();
+    sr_count_launch(2);
     return cudaGetLastError();
 }
 

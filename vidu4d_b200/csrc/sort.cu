@@ -29,49 +29,48 @@ struct SortPlan {
     int bits[SR_SORT_MAX_PASSES];
 };
 
-// One read of the keys builds the digit histograms of ALL passes; the LAST block to finish then exclusive-scans each
-// pass's histogram in place and decides which passes are identity permutations (what used to be a separate single-block
-// "plan" kernel and its launch latency).
 __global__ void __launch_bounds__(256)
 sort_histogram_kernel(const FrameStrides fs, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ num_rendered,
-                      long long capacity, SortPlan plan, uint32_t* __restrict__ hist, uint32_t* __restrict__ ctl) {
+                      long long capacity, SortPlan plan, uint32_t* __restrict__ hist) {
     const int f = blockIdx.y;
-    keys = fr(keys, fs.bin, f); num_rendered = fr(num_rendered, fs.nr, f); hist = fr(hist, fs.bin, f); ctl = fr(ctl, fs.bin, f);
+    keys = fr(keys, fs.bin, f); num_rendered = fr(num_rendered, fs.nr, f); hist = fr(hist, fs.bin, f);
     const uint32_t n = num_rendered[0];
-    const bool dead = (long long)n > capacity || n == 0;
+    if ((long long)n > capacity) return;
     __shared__ uint32_t sh[SR_SORT_MAX_PASSES * SR_SORT_BINS];
-    __shared__ uint32_t wsum[8];
-    __shared__ int skip_s[SR_SORT_MAX_PASSES];
-    __shared__ bool last_s;
+    for (int i = threadIdx.x; i < plan.npass * SR_SORT_BINS; i += 256) sh[i] = 0;
+    __syncthreads();
     const uint32_t per_block = 256 * 16;
     const uint32_t base = blockIdx.x * per_block;
-    if (!dead && base < n) {
-        for (int i = threadIdx.x; i < plan.npass * SR_SORT_BINS; i += 256) sh[i] = 0;
-        __syncthreads();
+    if (base >= n) return;
 #pragma unroll 4
-        for (int j = 0; j < 16; j++) {
-            const uint32_t i = base + j * 256 + threadIdx.x;
-            if (i < n) {
-                const uint64_t k = keys[i];
-                for (int p = 0; p < plan.npass; p++)
-                    atomicAdd(&sh[p * SR_SORT_BINS + (uint32_t)((k >> plan.shift[p]) & ((1u << plan.bits[p]) - 1u))], 1u);
-            }
+    for (int j = 0; j < 16; j++) {
+        const uint32_t i = base + j * 256 + threadIdx.x;
+        if (i < n) {
+            const uint64_t k = keys[i];
+            for (int p = 0; p < plan.npass; p++)
+                atomicAdd(&sh[p * SR_SORT_BINS + (uint32_t)((k >> plan.shift[p]) & ((1u << plan.bits[p]) - 1u))], 1u);
         }
-        __syncthreads();
-        for (int i = threadIdx.x; i < plan.npass * SR_SORT_BINS; i += 256)
-            if (sh[i]) atomicAdd(&hist[i], sh[i]);
     }
-    __threadfence();                                       // this block's contributions are visible before its ticket
     __syncthreads();
-    if (threadIdx.x == 0) last_s = atomicAdd(ctl + SR_CTL_TICKET_HIST, 1u) == gridDim.x - 1;
+    for (int i = threadIdx.x; i < plan.npass * SR_SORT_BINS; i += 256)
+        if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+
+// one block: exclusive-scan each pass's histogram in place, decide which passes are identities
+__global__ void __launch_bounds__(256)
+sort_plan_kernel(const FrameStrides fs, uint32_t* __restrict__ hist, uint32_t* __restrict__ ctl,
+                 const uint32_t* __restrict__ num_rendered, long long capacity, SortPlan plan) {
+    const int f = blockIdx.x;                       // one block per frame
+    hist = fr(hist, fs.bin, f); ctl = fr(ctl, fs.bin, f); num_rendered = fr(num_rendered, fs.nr, f);
+    const uint32_t n = num_rendered[0];
+    __shared__ uint32_t wsum[8];
+    __shared__ int skip_s[SR_SORT_MAX_PASSES];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x < SR_SORT_MAX_PASSES) skip_s[threadIdx.x] = 0;
     __syncthreads();
-    if (!last_s) return;
-    __threadfence();
-    // ---- plan (one thread per bin)
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool dead = (long long)n > capacity || n == 0;
     for (int p = 0; p < plan.npass; p++) {
-        const uint32_t v = __ldcg(hist + p * SR_SORT_BINS + threadIdx.x);
+        const uint32_t v = hist[p * SR_SORT_BINS + threadIdx.x];
         if (v == n || dead) skip_s[p] = 1;      // benign race: every writer writes 1
         uint32_t inc = v;
 #pragma unroll
@@ -230,61 +229,19 @@ onesweep_pass_kernel(const FrameStrides fs, uint64_t* __restrict__ keys0, uint64
 // of six, so one LDG.128 / STG.128 covers six whole records -- 480 contiguous bytes on the store side -- instead of 32
 // lanes each touching its own record at an 80-byte stride (r2a ncu: 24 % issue, 39 % DRAM, the load/store unit spent
 // 32 cycles per instruction on 32 distinct sectors).
-__device__ __forceinline__ void gather_warp(uint32_t n, uint32_t wbase, const uint64_t* __restrict__ keys0, const uint64_t* __restrict__ keys1,
-                                            const uint32_t* __restrict__ vals0, const uint32_t* __restrict__ vals1,
-                                            const uint32_t* __restrict__ ctl, const float4* __restrict__ srec,
-                                            float4* __restrict__ irec, uint2* __restrict__ ranges, int tiles_x);
-
 __global__ void __launch_bounds__(256)
 ranges_gather_kernel(const FrameStrides fs, const uint64_t* __restrict__ keys0, const uint64_t* __restrict__ keys1,
                      const uint32_t* __restrict__ vals0, const uint32_t* __restrict__ vals1,
                      const uint32_t* __restrict__ ctl, const uint32_t* __restrict__ num_rendered, long long capacity,
-                     const float4* __restrict__ srec, float4* __restrict__ irec, uint2* __restrict__ ranges, int tiles_x,
-                     int tiles, uint32_t* __restrict__ order) {
+                     const float4* __restrict__ srec, float4* __restrict__ irec, uint2* __restrict__ ranges, int tiles_x) {
     const int f = blockIdx.y;
     keys0 = fr(keys0, fs.bin, f); keys1 = fr(keys1, fs.bin, f); vals0 = fr(vals0, fs.bin, f); vals1 = fr(vals1, fs.bin, f);
     ctl = fr(ctl, fs.bin, f); num_rendered = fr(num_rendered, fs.nr, f); srec = fr(srec, fs.geom, f);
     irec = fr(irec, fs.bin, f); ranges = fr(ranges, fs.img, f);
-    order = fr(order, fs.img, f);
     const uint32_t n = num_rendered[0];
-    const bool dead = (long long)n > capacity;
+    if ((long long)n > capacity) return;
     const uint32_t wbase = (blockIdx.x * 256u + threadIdx.x) & ~31u;      // first instance of this warp
-    if (!dead && wbase < n) gather_warp(n, wbase, keys0, keys1, vals0, vals1, ctl, srec, irec, ranges, tiles_x);
-    // ---- the LAST block to finish builds the longest-list-first launch order of the composite kernels
-    __shared__ bool last_s;
-    __shared__ uint32_t cnt[33], start[33];
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) last_s = atomicAdd(const_cast<uint32_t*>(ctl) + SR_CTL_TICKET_GATHER, 1u) == gridDim.x - 1;
-    if (threadIdx.x < 33) cnt[threadIdx.x] = 0;
-    __syncthreads();
-    if (!last_s) return;
-    __threadfence();
-    // Longest-processing-time-first: tiles bucketed by floor(log2(len)), longest bucket first.  The CTA scheduler hands out
-    // work in blockIdx order, so the heavy tiles of an object-centric frame start first and the many light / empty ones
-    // fill the tail (round r1b ncu: SM busy cycles ranged 152K..548K with row-major order).
-    for (int t = threadIdx.x; t < tiles; t += 256) {
-        const uint2 r = __ldcg(ranges + t);
-        const uint32_t len = r.y - r.x;
-        atomicAdd(&cnt[len ? 32 - __clz(len) : 0], 1u);     // bucket 0 = empty, b = floor(log2(len)) + 1
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t acc = 0;
-        for (int b = 32; b >= 0; b--) { start[b] = acc; acc += cnt[b]; }
-    }
-    __syncthreads();
-    for (int t = threadIdx.x; t < tiles; t += 256) {
-        const uint2 r = __ldcg(ranges + t);
-        const uint32_t len = r.y - r.x;
-        order[atomicAdd(&start[len ? 32 - __clz(len) : 0], 1u)] = (uint32_t)t;
-    }
-}
-
-__device__ __forceinline__ void gather_warp(uint32_t n, uint32_t wbase, const uint64_t* __restrict__ keys0, const uint64_t* __restrict__ keys1,
-                                            const uint32_t* __restrict__ vals0, const uint32_t* __restrict__ vals1,
-                                            const uint32_t* __restrict__ ctl, const float4* __restrict__ srec,
-                                            float4* __restrict__ irec, uint2* __restrict__ ranges, int tiles_x) {
+    if (wbase >= n) return;                                                // whole warp out of range
     const int lane = threadIdx.x & 31;
     const uint32_t i = wbase + lane;
     const bool live = i < n;
@@ -345,6 +302,35 @@ __device__ __forceinline__ void gather_warp(uint32_t n, uint32_t wbase, const ui
     }
 }
 
+// Longest-processing-time-first launch order for the composite kernels: tiles bucketed by floor(log2(len)),
+// longest bucket first.  The CTA scheduler hands out work in blockIdx order, so the heavy tiles of an
+// object-centric frame start first and the many light / empty ones fill the tail (round r1b ncu: SM busy
+// cycles ranged 152K..548K with row-major order).
+__global__ void __launch_bounds__(1024)
+tile_order_kernel(const FrameStrides fs, const uint2* __restrict__ ranges, int tiles, uint32_t* __restrict__ order) {
+    ranges = fr(ranges, fs.img, (int)blockIdx.x);   // one block per frame
+    order = fr(order, fs.img, (int)blockIdx.x);
+    __shared__ uint32_t cnt[33], start[33];
+    if (threadIdx.x < 33) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    for (int t = threadIdx.x; t < tiles; t += 1024) {
+        const uint2 r = ranges[t];
+        const uint32_t len = r.y - r.x;
+        atomicAdd(&cnt[len ? 32 - __clz(len) : 0], 1u);     // bucket 0 = empty, b = floor(log2(len)) + 1
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t acc = 0;
+        for (int b = 32; b >= 0; b--) { start[b] = acc; acc += cnt[b]; }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < tiles; t += 1024) {
+        const uint2 r = ranges[t];
+        const uint32_t len = r.y - r.x;
+        order[atomicAdd(&start[len ? 32 - __clz(len) : 0], 1u)] = (uint32_t)t;
+    }
+}
+
 SortPlan make_plan(int key_bits) {
     SortPlan p{};
     int np = 0;
@@ -371,12 +357,14 @@ cudaError_t launch_sort(const FwdArgs& a) {
     const long long cap = (long long)a.bl.capacity;
     const int hblocks = (int)((cap + 4095) / 4096);
     { ProfileScope ps("sort_histogram", a.stream);
-      sort_histogram_kernel<<<dim3(hblocks, a.fs.frames), 256, 0, a.stream>>>(a.fs, k0, a.num_rendered_dev, cap, plan, hist, ctl); }
+      sort_histogram_kernel<<<dim3(hblocks, a.fs.frames), 256, 0, a.stream>>>(a.fs, k0, a.num_rendered_dev, cap, plan, hist); }
+    { ProfileScope ps("sort_plan", a.stream);
+      sort_plan_kernel<<<a.fs.frames, 256, 0, a.stream>>>(a.fs, hist, ctl, a.num_rendered_dev, cap, plan); }
     ProfileScope ps("onesweep_passes", a.stream);
     for (int p = 0; p < plan.npass; p++)
         onesweep_pass_kernel<<<dim3(a.bl.sort_tiles, a.fs.frames), SR_SORT_THREADS, 0, a.stream>>>(
             a.fs, k0, k1, v0, v1, hist, ctl, status, a.num_rendered_dev, p, plan.shift[p], plan.bits[p], a.bl.sort_tiles);
-    sr_count_launch(1 + plan.npass);
+    sr_count_launch(2 + plan.npass);
     return cudaGetLastError();
 }
 
@@ -389,8 +377,15 @@ cudaError_t launch_ranges_gather(const FwdArgs& a) {
         (const uint32_t*)(a.bin + a.bl.values[0]), (const uint32_t*)(a.bin + a.bl.values[1]),
         (const uint32_t*)(a.bin + a.bl.sort_ctl), a.num_rendered_dev, cap,
         (const float4*)(a.geom + a.gl.surfel_rec), (float4*)(a.bin + a.bl.inst_rec),
-        (uint2*)(a.img + a.il.ranges), a.il.tiles_x, a.il.tiles, (uint32_t*)(a.img + a.il.tile_order));
+        (uint2*)(a.img + a.il.ranges), a.il.tiles_x);
     sr_count_launch();
     return cudaGetLastError();
 }
 
+cudaError_t launch_tile_order(const FwdArgs& a) {
+    ProfileScope ps("tile_order", a.stream);
+    tile_order_kernel<<<a.fs.frames, 1024, 0, a.stream>>>(a.fs, (const uint2*)(a.img + a.il.ranges), a.il.tiles,
+                                                 (uint32_t*)(a.img + a.il.tile_order));
+    sr_count_launch();
+    return cudaGetLastError();
+}

@@ -116,10 +116,13 @@ class FlatSurfelModel(torch.nn.Module):
     # ---- densification statistics (gaussian_model.py:450-452, trainer.py:553-560) ----------------------------------
     @torch.no_grad()
     def add_densification_stats(self, viewspace_grad, update_filter, radii=None):
-        self.xyz_gradient_accum[update_filter] += torch.norm(viewspace_grad[update_filter], dim=-1, keepdim=True)
-        self.denom[update_filter] += 1
+        """Same values as the reference's boolean-mask updates, written with masks and in-place ops: fixed shapes and
+        stable addresses, so the call can sit inside a captured CUDA graph (a boolean index would need a host sync)."""
+        f = update_filter.unsqueeze(-1).to(torch.float32)
+        self.xyz_gradient_accum.add_(torch.norm(viewspace_grad, dim=-1, keepdim=True) * f)
+        self.denom.add_(f)
         if radii is not None:
-            self.max_radii2D[update_filter] = torch.max(self.max_radii2D[update_filter], radii[update_filter].float())
+            self.max_radii2D.copy_(torch.where(update_filter, torch.max(self.max_radii2D, radii.float()), self.max_radii2D))
 
     # ---- densify / prune in one gather (gaussian_model.py:376-446) ------------------------------------------------
     @torch.no_grad()

@@ -40,15 +40,7 @@ from vidu4d_b200.synthetic import SurfelCloud, object_scene, projection_matrix  
 from vidu4d_b200.warp import bob_warp  # noqa: E402
 
 
-def qmul(a, b):
-    aw, ax, ay, az = a.unbind(-1)
-    bw, bx, by, bz = b.unbind(-1)
-    return torch.stack((aw * bw - ax * bx - ay * by - az * bz, aw * bx + ax * bw + ay * bz - az * by,
-                        aw * by - ax * bz + ay * bw + az * bx, aw * bz + ax * by - ay * bx + az * bw), -1)
-
-
-def qconj(q):
-    return torch.cat((q[..., :1], -q[..., 1:]), -1)
+from vidu4d_b200.warp import _qconj as qconj, _qmul as qmul  # noqa: E402  (Hamilton product in 4 kernels, not 28)
 
 
 def qapply(q, p):

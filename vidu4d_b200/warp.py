@@ -15,15 +15,31 @@ import torch
 from . import _capi
 
 
+# Hamilton product as ONE gather + two multiplies + one sum (out_i = sum_j SGN[i][j] * a[IDX[i][j]] * b[j]) instead of the
+# 28 elementwise kernels (and ~60 in the backward) of the unbind / stack formulation: the bone tables are tens of floats, so
+# their cost is pure launch count -- ~600 of the ~800 kernels of a captured Stage-3 step before this (r2h launch list).
+_Q_IDX = ((0, 1, 2, 3), (1, 0, 3, 2), (2, 3, 0, 1), (3, 2, 1, 0))
+_Q_SGN = ((1.0, -1.0, -1.0, -1.0), (1.0, 1.0, -1.0, 1.0), (1.0, 1.0, 1.0, -1.0), (1.0, -1.0, 1.0, 1.0))
+_q_tables: dict = {}
+
+
+def _qt(device, dtype):
+    key = (str(device), dtype)
+    t = _q_tables.get(key)
+    if t is None:
+        t = (torch.tensor(_Q_IDX, device=device), torch.tensor(_Q_SGN, device=device, dtype=dtype),
+             torch.tensor((1.0, -1.0, -1.0, -1.0), device=device, dtype=dtype))
+        _q_tables[key] = t
+    return t
+
+
 def _qmul(a, b):
-    aw, ax, ay, az = a.unbind(-1)
-    bw, bx, by, bz = b.unbind(-1)
-    return torch.stack((aw * bw - ax * bx - ay * by - az * bz, aw * bx + ax * bw + ay * bz - az * by,
-                        aw * by - ax * bz + ay * bw + az * bx, aw * bz + ax * by - ay * bx + az * bw), -1)
+    idx, sgn, _ = _qt(a.device, a.dtype)
+    return ((a[..., idx] * sgn) * b[..., None, :]).sum(-1)
 
 
 def _qconj(q):
-    return torch.cat((q[..., :1], -q[..., 1:]), -1)
+    return q * _qt(q.device, q.dtype)[2]
 
 
 class _BobWarp(torch.autograd.Function):

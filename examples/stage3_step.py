@@ -40,7 +40,19 @@ from vidu4d_b200.synthetic import SurfelCloud, object_scene, projection_matrix  
 from vidu4d_b200.warp import bob_warp  # noqa: E402
 
 
-from vidu4d_b200.warp import _qconj as qconj, _qmul as qmul  # noqa: E402  (Hamilton product in 4 kernels, not 28)
+from vidu4d_b200.warp import _qconj as qconj, _qmul as _qmul_small  # noqa: E402
+
+
+def qmul(a, b):
+    """Hamilton product.  Small operands (bone tables) take the 4-kernel gather form; the big (M,P,B,4) blends of the
+    PyTorch warp take the component form, which is the faster of the two there (no 4x intermediate) -- the reference
+    backend gets whichever PyTorch formulation is quickest for its tensor sizes."""
+    if max(a.numel(), b.numel()) <= (1 << 16):
+        return _qmul_small(a, b)
+    aw, ax, ay, az = a.unbind(-1)
+    bw, bx, by, bz = b.unbind(-1)
+    return torch.stack((aw * bw - ax * bx - ay * by - az * bz, aw * bx + ax * bw + ay * bz - az * by,
+                        aw * by - ax * bz + ay * bw + az * bx, aw * bz + ax * by - ay * bx + az * bw), -1)
 
 
 def qapply(q, p):

@@ -189,6 +189,51 @@ def test_graphed_step_recaptures_on_growth_and_on_overflow(dev):
         RZ._pending.clear()
 
 
+def test_graphed_step_growth_200k_to_300k(dev):
+    """The Stage-3 scale of the densification path (gs/scene/gaussian_model.py:291-356, lab4d/engine/trainer.py:562-568):
+    a captured batched step over 200 K surfels, half of them densified (clone or split: +1 surfel each) -> 300 K, the
+    step re-captured with re-sized buffers, image and gradient equal to an eager run on the grown model."""
+    from vidu4d_b200 import rasterizer as RZ
+    from vidu4d_b200.graph import GraphedStep
+    from vidu4d_b200.renderer import PipelineParams, make_camera, render_fused
+    m = _model(200000, dev, seed=8)
+    cam = make_camera(256, 256, 2 * np.arctan(0.5), 2 * np.arctan(0.5), device=dev)
+    bg = torch.zeros(3, device=dev)
+    img = torch.zeros((3, 256, 256), device=dev)
+
+    def body():
+        m.zero_grad_flat()
+        out = render_fused(cam, m, PipelineParams(), bg)
+        (out["render"].mean() + 0.1 * out["rend_dist"].mean()).backward()
+        img.copy_(out["render"].detach())
+    step = GraphedStep(body, key=lambda: m.P, device=dev)
+    try:
+        step(); step()
+        assert step.captures == 1
+        with torch.no_grad():
+            m._opacity.clamp_(min=-2.0)                    # nobody falls under the opacity prune threshold
+        m.denom += 1.0
+        m.xyz_gradient_accum[:100000] += 1.0                # exactly half of the surfels densify
+        info = m.densify_and_prune(2e-4, 0.005, 1.0, None)
+        assert info["cloned"] + info["split"] == 100000 and info["pruned"] == 0 and m.P == 300000
+        m.adam_step()                                       # the optimizer state followed the new layout
+        step()
+        assert step.captures == 2 and m.grad_flat.numel() == m.flat.numel() == 300000 * 58
+        g_graph = m.grad_flat.clone()
+        i_graph = img.clone()
+        RZ.check_overflow()
+        RZ.set_sync_mode(True)
+        m.zero_grad_flat()
+        out = render_fused(cam, m, PipelineParams(), bg)
+        (out["render"].mean() + 0.1 * out["rend_dist"].mean()).backward()
+        assert torch.equal(i_graph, out["render"].detach())
+        rel = float((g_graph - m.grad_flat).norm() / m.grad_flat.norm())
+        assert rel < 1e-5, rel                              # atomics order differs run to run; nothing else does
+    finally:
+        RZ.set_sync_mode(True)
+        RZ._pending.clear()
+
+
 @pytest.mark.parametrize("P,kind", [(20000, "sphere"), (5000, "blob"), (4, "tiny"), (3000, "dups")])
 def test_knn_mean_dist2_matches_brute_force(P, kind, dev):
     """distCUDA2 (simple_knn.cu:132-218): exact 3-NN mean squared distance, duplicates included, against brute force."""

@@ -43,8 +43,6 @@
 #define SR_G_M2D 16
 
 #define SR_CONTRIB_STAGE_WORDS 256  // 8 sub-tiles x 32 pixels, one 32-bit instance mask each (1 KB per stage)
-#define SR_LOCAL_SORT_CAP 8192   // max instances of one tile the tile-local sort holds in shared memory
-#define SR_STATUS_SORT_CAP 8u     // status bit: a tile exceeded it -- re-run with the global onesweep path
 #define SR_SORT_MAX_PASSES 8
 #define SR_SORT_RADIX_BITS 8
 #define SR_SORT_BINS 256
@@ -67,7 +65,7 @@ struct GeomLayout {
     int nblocks;
 };
 struct ImageLayout {
-    size_t final_T, n_contrib, ranges, tile_last, tile_order, tile_count, tile_cursor, total;
+    size_t final_T, n_contrib, ranges, tile_last, tile_order, total;
     int tiles_x, tiles_y, tiles;
 };
 struct BinLayout {
@@ -100,8 +98,6 @@ static inline __host__ __device__ ImageLayout image_layout(int W, int H) {
     L.ranges = o;    o = sr_align_up(o + (size_t)L.tiles * 8);
     L.tile_last = o; o = sr_align_up(o + (size_t)L.tiles * 8 * 4);   // per 8x4 sub-tile: deepest contributor
     L.tile_order = o; o = sr_align_up(o + (size_t)L.tiles * 4);       // tiles, longest instance list first
-    L.tile_count = o; o = sr_align_up(o + (size_t)L.tiles * 4);       // tile-local sort: instances per tile
-    L.tile_cursor = o; o = sr_align_up(o + (size_t)L.tiles * 4);      // tile-local sort: scatter cursors
     L.total = o;
     return L;
 }

@@ -16,6 +16,7 @@
 //     scattered through shared memory so the global stores are contiguous per bin.
 //   The instance count R lives only on the device (no D2H sync in the forward): grids are sized from the
 //   buffer CAPACITY and surplus blocks exit on the first load of R.
+#include <cstdlib>
 #include "composite_common.cuh"
 
 namespace {
@@ -95,16 +96,24 @@ sort_plan_kernel(const FrameStrides fs, uint32_t* __restrict__ hist, uint32_t* _
     }
 }
 
-__global__ void __launch_bounds__(SR_SORT_THREADS)
+template <int MINB>
+__global__ void __launch_bounds__(SR_SORT_THREADS, MINB)
 onesweep_pass_kernel(const FrameStrides fs, uint64_t* __restrict__ keys0, uint64_t* __restrict__ keys1,
                      uint32_t* __restrict__ vals0, uint32_t* __restrict__ vals1, const uint32_t* __restrict__ hist,
                      uint32_t* __restrict__ ctl, uint32_t* __restrict__ status, const uint32_t* __restrict__ num_rendered,
-                     int pass, int shift, int bits, int sort_tiles) {
-    const int f = blockIdx.y;
+                     int pass, int shift, int bits, int sort_tiles, int interleave) {
+    // Block -> (frame, slot).  Interleaved: consecutive blocks belong to different frames, so the ~300 blocks resident at
+    // a time hold only ~300 / frames consecutive tiles of any one frame and the look-back chain inside a wave is that
+    // short (all tiles of a 0.5 M-key frame would otherwise start together and tile t would walk back over t tiles).
+    const int f = interleave ? (int)(blockIdx.x % (unsigned)fs.frames) : (int)(blockIdx.x / (unsigned)sort_tiles);
+    const uint32_t slot = interleave ? blockIdx.x / (unsigned)fs.frames : blockIdx.x % (unsigned)sort_tiles;
     keys0 = fr(keys0, fs.bin, f); keys1 = fr(keys1, fs.bin, f); vals0 = fr(vals0, fs.bin, f); vals1 = fr(vals1, fs.bin, f);
     hist = fr(hist, fs.bin, f); ctl = fr(ctl, fs.bin, f); status = fr(status, fs.bin, f); num_rendered = fr(num_rendered, fs.nr, f);
-    if (ctl[SR_CTL_SKIP + pass]) return;
+    const uint32_t skip = ctl[SR_CTL_SKIP + pass];
     const uint32_t n = num_rendered[0];
+    // the grid is sized from the buffer capacity: blocks beyond the tiles this frame needs leave before taking a ticket
+    // (exactly ceil(n / TILE) blocks stay, so every ticket below that is handed out)
+    if (skip || (unsigned long long)slot * SR_SORT_TILE >= n) return;
     __shared__ uint64_t keys_s[SR_SORT_TILE];
     __shared__ uint32_t vals_s[SR_SORT_TILE];
     __shared__ uint32_t whist[8][SR_SORT_BINS];
@@ -361,9 +370,19 @@ cudaError_t launch_sort(const FwdArgs& a) {
     { ProfileScope ps("sort_plan", a.stream);
       sort_plan_kernel<<<a.fs.frames, 256, 0, a.stream>>>(a.fs, hist, ctl, a.num_rendered_dev, cap, plan); }
     ProfileScope ps("onesweep_passes", a.stream);
-    for (int p = 0; p < plan.npass; p++)
-        onesweep_pass_kernel<<<dim3(a.bl.sort_tiles, a.fs.frames), SR_SORT_THREADS, 0, a.stream>>>(
-            a.fs, k0, k1, v0, v1, hist, ctl, status, a.num_rendered_dev, p, plan.shift[p], plan.bits[p], a.bl.sort_tiles);
+    // 3 resident blocks per SM (<= 85 registers, no spills) instead of 2: the pass is latency bound (ticket, key loads,
+    // look-back), r2g ncu: 24 % warps active, 15 % DRAM.  SURFEL_SORT_MINB=2 selects the old bound for A/B runs.
+    static const int minb = [] { const char* e = getenv("SURFEL_SORT_MINB"); return e && atoi(e) == 2 ? 2 : 3; }();
+    static const int inter = [] { const char* e = getenv("SURFEL_SORT_INTERLEAVE"); return e && atoi(e) == 0 ? 0 : 1; }();
+    const unsigned blocks = (unsigned)a.bl.sort_tiles * (unsigned)a.fs.frames;
+    for (int p = 0; p < plan.npass; p++) {
+        if (minb == 2)
+            onesweep_pass_kernel<2><<<blocks, SR_SORT_THREADS, 0, a.stream>>>(
+                a.fs, k0, k1, v0, v1, hist, ctl, status, a.num_rendered_dev, p, plan.shift[p], plan.bits[p], a.bl.sort_tiles, inter);
+        else
+            onesweep_pass_kernel<3><<<blocks, SR_SORT_THREADS, 0, a.stream>>>(
+                a.fs, k0, k1, v0, v1, hist, ctl, status, a.num_rendered_dev, p, plan.shift[p], plan.bits[p], a.bl.sort_tiles, inter);
+    }
     sr_count_launch(2 + plan.npass);
     return cudaGetLastError();
 }

@@ -392,6 +392,8 @@ def main():
             step_fn(s)
         if step_fn is step_dev and BATCH:
             drain()
+        if getattr(step_fn, "drain", None) is not None:
+            step_fn.drain()
         sync_all(world)
         starts = [torch.cuda.Event(enable_timing=True) for _ in range(nsteps)]
         ends = [torch.cuda.Event(enable_timing=True) for _ in range(nsteps)]
@@ -403,6 +405,8 @@ def main():
             ends[s].record()
         if step_fn is step_dev and BATCH:
             drain()                                   # the last step's overflow check (inside the wall-clock, after its event)
+        if getattr(step_fn, "drain", None) is not None:
+            step_fn.drain()                           # e2e: the last step's loss readback + overflow check
         sync_all(world)
         wall = (time.perf_counter() - t0) * 1e3
         per = [a.elapsed_time(b) for a, b in zip(starts, ends)]
@@ -471,19 +475,28 @@ def main():
     fg = D.FlatGrads(params)
     opt = torch.optim.Adam(params, lr=1e-7, fused=True)
     targets_h = torch.rand((F, 3, RES, RES), generator=torch.Generator().manual_seed(5)).pin_memory()
-    cam_h = torch.empty((F, 2, 4, 4)).pin_memory()       # viewmatrix, full_proj per frame
-    cps_hh = torch.empty((F, 3)).pin_memory()
-    loss_h = torch.empty((1,)).pin_memory()
+    # host side of a step's inputs: per-view camera blocks live in pinned tables; every step gathers ITS F views into a
+    # pinned staging block (two of them, so that the host can stage step k+1 while the copy engine still reads step k's)
+    cam_tab_h = torch.from_numpy(np.stack([np.stack([vms_h[v], pms_h[v]]) for v in range(NVIEWS)]).astype(np.float32)).pin_memory()
+    cps_tab_h = torch.from_numpy(np.ascontiguousarray(cps_h, dtype=np.float32).reshape(NVIEWS, 3)).pin_memory()
+    cam_hs = [torch.empty((F, 2, 4, 4)).pin_memory() for _ in range(2)]      # viewmatrix, full_proj per frame
+    cps_hs = [torch.empty((F, 3)).pin_memory() for _ in range(2)]
+    loss_hs = [torch.empty((1,)).pin_memory() for _ in range(2)]
+    cam_h, cps_hh, loss_h = cam_hs[0], cps_hs[0], loss_hs[0]
     h2d = targets_h.numel() * 4 + cam_h.numel() * 4 + cps_hh.numel() * 4
     fov = 2.0 * float(np.arctan(TAN))
 
     tg = torch.empty((F, 3, RES, RES), device=device); cam = torch.empty((F, 2, 4, 4), device=device); cp = torch.empty((F, 3), device=device)
     tot = torch.zeros((), device=device)
 
-    def fill_host(step):
-        for f in range(F):
-            v = view_of(step, f)
-            cam_h[f, 0] = torch.from_numpy(vms_h[v]); cam_h[f, 1] = torch.from_numpy(pms_h[v]); cps_hh[f] = torch.from_numpy(cps_h[v])
+    view_idx = {}
+
+    def fill_host(step, slot=0):
+        idx = view_idx.get(step)
+        if idx is None:
+            idx = view_idx[step] = torch.tensor([view_of(step, f) for f in range(F)], dtype=torch.int64)
+        torch.index_select(cam_tab_h, 0, idx, out=cam_hs[slot])
+        torch.index_select(cps_tab_h, 0, idx, out=cps_hs[slot])
 
     e2e_streams = [1]
     tots = [torch.zeros((), device=device) for _ in range(8)]
@@ -521,10 +534,10 @@ def main():
     if BATCH:
         from vidu4d_b200.renderer import BatchCameras, render_loss_batch
 
-        def body_batch():
+        def body_batch(slot=0):
             """H2D of this step's inputs -> ONE batched rasterize + fused post-processing + losses -> ONE batched backward."""
             main = torch.cuda.current_stream()
-            cam.copy_(cam_h, non_blocking=True); cp.copy_(cps_hh, non_blocking=True)
+            cam.copy_(cam_hs[slot], non_blocking=True); cp.copy_(cps_hs[slot], non_blocking=True)
             side[0].wait_stream(main)
             with torch.cuda.stream(side[0]):           # the step's target images upload beside the rasterizer forward
                 tg.copy_(targets_h, non_blocking=True)
@@ -553,14 +566,51 @@ def main():
         return float(loss_h[0])
 
     graph, e2e_mode = None, "eager"
+    # Pipelined e2e loop (ours, batch mode): two captures of the step, each bound to its own pinned staging block, loss
+    # word and status words.  The host stages + queues step k (H2D, render, losses, backward, all-reduce, Adam, D2H of the
+    # loss), THEN waits for step k-1's event, reads its loss and checks its overflow words -- every step still uploads its
+    # inputs and has its result read on the host, but the GPU never idles while the host prepares the next step.
+    e2e_graphs = [None, None]
+    e2e_done = [torch.cuda.Event(), torch.cuda.Event()]
+    e2e_inflight = [None]
+    pipelined = [False]
+
+    def drain_e2e():
+        """Host side of the step still in flight: wait for it, check its overflow words, return its loss."""
+        k = e2e_inflight[0]
+        if k is None:
+            return None
+        e2e_done[k].synchronize()
+        RZ._pending[:] = e2e_graphs[k].watch
+        RZ.check_overflow(keep=True, sync=False)
+        e2e_inflight[0] = None
+        return float(loss_hs[k][0])
 
     def step_e2e(step):
+        if pipelined[0]:
+            k = step & 1
+            fill_host(step, k)
+            e2e_graphs[k].replay()
+            fg.allreduce_(average_over=F * world)
+            if not freeze[0]:
+                opt.step()
+            loss_hs[k].copy_(tot.reshape(1), non_blocking=True)
+            e2e_done[k].record()
+            last = drain_e2e()              # step k-1: finished long ago
+            e2e_inflight[0] = k
+            return last
         fill_host(step)
         if graph is not None:
             graph.replay()
         else:
             body()
         return tail()
+    step_e2e.drain = drain_e2e
+
+    def step_e2e_sync(step):
+        """One step, its loss returned (the check below compares single steps)."""
+        r = step_e2e(step)
+        return drain_e2e() if pipelined[0] else r
 
     if args.impl == "ours" and not args.no_graph:
         # The sync-free forward makes the whole step capturable: one cudaGraphLaunch replaces ~150 small launches.
@@ -585,7 +635,23 @@ def main():
                     body()
                 graph = gph
                 graph.watch = list(RZ._pending)
-                e2e_mode = (f"cuda_graph(H2D + batched render_loss_batch + backward, 1 stream) + eager all-reduce/Adam/readback" if BATCH else
+                if BATCH:       # second copy, bound to staging slot 1
+                    RZ._pending.clear()
+                    RZ.reserve_host_slots(F + 4)
+                    with torch.cuda.stream(warm):
+                        fill_host(1, 1); body_batch(1); RZ.check_overflow()
+                    torch.cuda.current_stream().wait_stream(warm)
+                    torch.cuda.synchronize()
+                    RZ.reserve_host_slots(F + 4)
+                    gph2 = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(gph2):
+                        body_batch(1)
+                    gph2.watch = list(RZ._pending)
+                    e2e_graphs[0], e2e_graphs[1] = gph, gph2
+                    pipelined[0] = True
+                    RZ._pending[:] = graph.watch
+                e2e_mode = (f"2 x cuda_graph(H2D + batched render_loss_batch + backward) used alternately + all-reduce/Adam/loss D2H; "
+                            f"step k-1's loss is read and its overflow words checked after step k is queued" if BATCH else
                             f"cuda_graph(H2D+render+loss+backward, {ns_try} stream(s)) + eager all-reduce/Adam/readback")
                 break
             except Exception as ex:   # pragma: no cover
@@ -603,11 +669,11 @@ def main():
         if graph is None and args.e2e_streams > 1:
             e2e_streams[0] = args.e2e_streams          # eager multi-stream (only for debugging the check)
         freeze[0] = True                                # same parameters for every evaluation of the check
-        l_mode = step_e2e(1000)
+        l_mode = step_e2e_sync(1000)
         torch.cuda.synchronize()
         g_mode = fg.flat.clone()
-        keep_graph, keep_ns = graph, e2e_streams[0]
-        graph, e2e_streams[0] = None, 1
+        keep_graph, keep_ns, keep_pipe = graph, e2e_streams[0], pipelined[0]
+        graph, e2e_streams[0], pipelined[0] = None, 1, False
         RZ._pending.clear()
         # the eager leg is round 1's per-frame path: render_fused() + the torch loss expressions + autograd -- an
         # independent evaluation of what the batched fused-loss step computes
@@ -618,7 +684,7 @@ def main():
         l_eager2 = step_e2e(1000)
         torch.cuda.synchronize()
         g_eager2 = fg.flat.clone()
-        graph, e2e_streams[0] = keep_graph, keep_ns
+        graph, e2e_streams[0], pipelined[0] = keep_graph, keep_ns, keep_pipe
         body_sel[0] = body_batch if BATCH else body_frames
         RZ._pending[:] = graph.watch if graph is not None else []
         freeze[0] = False
@@ -632,6 +698,18 @@ def main():
     e2e_total = max_over_ranks(e2e_total, world, device)
     e2e_value = frames / (e2e_total * 1e-3)
     clocks = sampler.stop() if rank == 0 else None
+    if os.environ.get("BENCH_PROFILE_E2E") and args.impl == "ours":
+        # launch list of the e2e step for `ncu --profile-from-start off --metrics gpu__time_duration.sum`: two EAGER steps
+        # (graph replays hide the kernels from the profiler's range) between cudaProfilerStart / Stop
+        keep = (graph, pipelined[0])
+        graph, pipelined[0] = None, False
+        RZ._pending.clear()
+        step_e2e(2000); torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step_e2e(2001); step_e2e(2002); torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        graph, pipelined[0] = keep
+        RZ._pending[:] = graph.watch if graph is not None else []
 
     # ---------------- per-kernel profile + roofline (ours only) ----------------
     roofline, kernels = None, None

@@ -61,6 +61,8 @@ def parse():
     ap.add_argument("--cpu-frames", type=int, default=8, help="frames of the cpu_baseline sample after one warm-up frame (0 = skip)")
     ap.add_argument("--mode", default="batch", choices=["batch", "streams"], help="ours: one batched launch set per step, or F single-frame calls over --streams CUDA streams")
     ap.add_argument("--no-value-graph", action="store_true", help="keep the value-arm step eager (no CUDA-graph capture)")
+    ap.add_argument("--split-features", action="store_true", help="e2e model keeps the reference's _features_dc / _features_rest "
+                    "pair (one torch.cat per step + the split of its gradient) instead of one (P,16,3) SH parameter")
     ap.add_argument("--no-variants", action="store_true", help="skip the 1- and 2-frame-per-call variants of the value arm")
     ap.add_argument("--split", type=int, default=1, help="batch mode: render the step's frames as this many sub-batches on parallel "
                     "streams inside the captured step (bandwidth-bound kernels of one overlap the composites of another)")
@@ -178,7 +180,8 @@ def main():
         _capi.load()   # fail loudly if the CUDA library is missing
 
     scene = object_scene(P, seed=0, opacity=args.opacity, center=(0.0, 0.0, 0.0))
-    cloud = SurfelCloud(scene, device)
+    # SH rows stored as one (P,16,3) parameter (both arms): no per-step concatenation of _features_dc / _features_rest
+    cloud = SurfelCloud(scene, device, fused_features=not args.split_features)
     vms_h, pms_h, cps_h = build_views(device)
     vms = torch.from_numpy(vms_h).to(device); pms = torch.from_numpy(pms_h).to(device); cps = torch.from_numpy(cps_h).to(device)
     bg = torch.zeros(3, device=device)
@@ -239,6 +242,11 @@ def main():
     accs = [views(stack[k]) for k in range(NS)]
     flat_views = views(flat_acc)
     flat_outs = dict(zip(("dL_dmeans3D", "dL_dsh", "dL_dopacity", "dL_dscales", "dL_drotations"), flat_views))
+    # second flat gradient buffer: the two captured value-arm steps each write their own, so that step k's all-reduce can
+    # run on the communication stream while step k+1 computes (multi-GPU only; see step_dev)
+    flat_acc2 = torch.zeros((nflt,), device=device) if (BATCH and world > 1) else flat_acc
+    flat_outs2 = dict(zip(("dL_dmeans3D", "dL_dsh", "dL_dopacity", "dL_dscales", "dL_drotations"), views(flat_acc2)))
+    flat_accs, flat_outss = [flat_acc, flat_acc2], [flat_outs, flat_outs2]
     GIDX = (3, 5, 2, 6, 7)      # gr = (dmeans2D, dcolors, dopacity, dmeans3D, dtransMat, dsh, dscales, drots)
     step_ctr = torch.zeros((), dtype=torch.int64, device=device)      # lives on the device: the captured step advances it
     ar = torch.arange(F, device=device)
@@ -252,8 +260,9 @@ def main():
     split_outs = [dict(zip(("dL_dmeans3D", "dL_dsh", "dL_dopacity", "dL_dscales", "dL_drotations"), views(split_rows[k])))
                   for k in range(SPLIT)] if SPLIT > 1 else None
 
-    def batch_body(fpc=None):
-        """One batched forward+backward of `fpc` frames (default F) + the sum over frames into the flat gradient."""
+    def batch_body(fpc=None, slot=0):
+        """One batched forward+backward of `fpc` frames (default F) + the sum over frames into the flat gradient
+        (buffer `slot`)."""
         n = F if fpc is None else fpc
         idx = (step_ctr * (world * F) + rank * F + ar[:n]) % NVIEWS
         step_ctr.add_(1)
@@ -281,7 +290,7 @@ def main():
         # directly in the flat buffer the all-reduce runs over
         gr = C.rasterize_gaussians_backward_batch(bg, t_in["means3D"], o[3], e, t_in["scales"], t_in["rots"], 1.0, vm_b, pm_b,
                                                   TAN, TAN, dLc_b[:n], dLo_b[:n], t_in["shs"], 3, cp_b, o[4], o[5], o[6],
-                                                  sum_shared=True, want_transmat=False, outs=flat_outs if n == F else None)
+                                                  sum_shared=True, want_transmat=False, outs=flat_outss[slot] if n == F else None)
         if n != F:      # the 1- and 2-frames-per-call variants: several calls per step accumulate into the flat buffer
             for a_, gi in zip(flat_views, GIDX):
                 a_.add_(gr[gi].reshape(a_.shape))
@@ -302,6 +311,16 @@ def main():
             RZ.check_overflow(keep=True, sync=False)
             inflight[0] = None
 
+    comm_stream = torch.cuda.Stream(device=device)
+    ar_done = [torch.cuda.Event(), torch.cuda.Event()]
+    ar_pending = [False, False]
+
+    def flush_allreduce():
+        """Make the current stream wait for any all-reduce still running on the communication stream."""
+        for k in range(2):
+            if ar_pending[k]:
+                torch.cuda.current_stream().wait_event(ar_done[k]); ar_pending[k] = False
+
     def step_dev(step):
         R_last = 0
         if BATCH:
@@ -309,7 +328,17 @@ def main():
                 k = step & 1
                 value_graphs[k].replay()
                 if world > 1:
-                    torch.distributed.all_reduce(flat_acc)
+                    # step k's all-reduce (its own flat buffer) goes to the communication stream and overlaps step k+1's
+                    # compute; this step's timed interval ends only after the PREVIOUS step's all-reduce has finished, so
+                    # every exchange lies inside a timed interval (the last one is flushed by step_dev.flush)
+                    main = torch.cuda.current_stream()
+                    comm_stream.wait_stream(main)
+                    with torch.cuda.stream(comm_stream):
+                        torch.distributed.all_reduce(flat_accs[k])
+                        ar_done[k].record()
+                    if ar_pending[1 - k]:
+                        main.wait_event(ar_done[1 - k]); ar_pending[1 - k] = False
+                    ar_pending[k] = True
                 done_ev[k].record()
                 drain()                     # step k-1 (the other graph): its words landed long ago
                 inflight[0] = k
@@ -382,15 +411,18 @@ def main():
     value_mode = "eager"
     value_graphs = [None, None]
     if BATCH and not args.no_value_graph:
-        value_graphs = [capture(batch_body, "the value-arm step"), capture(batch_body, "the value-arm step (second copy)")]
+        value_graphs = [capture(lambda: batch_body(slot=0), "the value-arm step"),
+                        capture(lambda: batch_body(slot=1), "the value-arm step (second copy)")]
         value_graph[0] = value_graphs[0] if all(g is not None for g in value_graphs) else None
         value_mode = ("2 x cuda_graph(batched forward+backward+frame-sum), overflow check of step k-1 after step k is queued"
+                      + ("; step k's all-reduce (own flat buffer, communication stream) overlaps step k+1's compute" if world > 1 else "")
                       if value_graph[0] is not None else "eager (capture failed)")
 
     def timed(step_fn, nsteps, nwarm):
         for s in range(nwarm):
             step_fn(s)
         if step_fn is step_dev and BATCH:
+            flush_allreduce()
             drain()
         if getattr(step_fn, "drain", None) is not None:
             step_fn.drain()
@@ -402,6 +434,8 @@ def main():
             flush.fill_(s & 255)                      # L2 flush between timed iterations (not timed)
             starts[s].record()
             step_fn(nwarm + s)
+            if s == nsteps - 1 and step_fn is step_dev and BATCH:
+                flush_allreduce()                     # the last step's exchange ends inside its own timed interval
             ends[s].record()
         if step_fn is step_dev and BATCH:
             drain()                                   # the last step's overflow check (inside the wall-clock, after its event)
@@ -830,7 +864,9 @@ def main():
             "e2e": {"value": round(e2e_value, 2), "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
                     "mode": e2e_mode, "check_vs_eager": e2e_check, "api": "render_loss_batch" if BATCH else ("render_fused" if render is render_fused else "render"),
                     "what": "render() -> L1+normal+distortion loss -> backward -> (all-reduce) -> fused Adam; per step the "
-                            "cameras + target images come from pinned host memory, the loss is read back"},
+                            "cameras + target images come from pinned host memory, the loss is read back",
+                    "model": "SurfelCloud, SH rows as " + ("_features_dc/_features_rest (torch.cat per step)" if args.split_features
+                                                           else "one (P,16,3) parameter (both arms)")},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels_ms": kernels, "variants": variants,
             "cpu_baseline": cpu_baseline, "reference_cuda": reference_cuda, "wall_ms_timed_region": round(wall_ms, 1),
         }

@@ -33,6 +33,12 @@ def init_distributed(backend: str | None = None, device: torch.device | None = N
         kw = {}
         if backend == "nccl" and device is not None:
             kw["device_id"] = device
+        if backend == "nccl":
+            # the collective's CTAs must be resident on every rank before it can progress: a high-priority communication
+            # stream lets them in ahead of the queued compute CTAs when an all-reduce overlaps the next step's kernels
+            opts = dist.ProcessGroupNCCL.Options()
+            opts.is_high_priority_stream = True
+            kw["pg_options"] = opts
         dist.init_process_group(backend=backend, init_method="env://", rank=rank, world_size=world, **kw)
     return rank, world
 

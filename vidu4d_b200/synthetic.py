@@ -162,14 +162,21 @@ class SurfelCloud(torch.nn.Module):
     raw parameters + activations.  Parameter list and order follow the Stage-3 gs_optimizer
     (lab4d/engine/trainer.py:243-251)."""
 
-    def __init__(self, scene: Scene, device="cuda"):
+    def __init__(self, scene: Scene, device="cuda", fused_features: bool = False):
+        """fused_features: keep the SH rows as ONE (P, 16, 3) parameter instead of the reference's _features_dc /
+        _features_rest pair (gaussian_model.py:98-118 concatenates the pair on every get_features; a model that stores
+        the rows the way the rasterizer reads them skips that copy and the split of its gradient)."""
         super().__init__()
         t = lambda a: torch.nn.Parameter(torch.from_numpy(np.ascontiguousarray(a)).to(device))  # noqa: E731
         self.max_sh_degree = 3
         self.active_sh_degree = scene.sh_degree
         self._xyz = t(scene.means3D)
-        self._features_dc = t(scene.shs[:, :1])
-        self._features_rest = t(scene.shs[:, 1:])
+        self.fused_features = bool(fused_features)
+        if self.fused_features:
+            self._features = t(scene.shs)
+        else:
+            self._features_dc = t(scene.shs[:, :1])
+            self._features_rest = t(scene.shs[:, 1:])
         self._scaling = t(np.log(scene.scales))
         self._rotation = t(scene.rotations)
         op = np.clip(scene.opacities, 1e-6, 1 - 1e-6)
@@ -193,10 +200,14 @@ class SurfelCloud(torch.nn.Module):
 
     @property
     def get_features(self):
+        if self.fused_features:
+            return self._features
         return torch.cat((self._features_dc, self._features_rest), dim=1)
 
     def get_covariance(self, scaling_modifier=1.0):
         raise NotImplementedError("precomputed covariance is not supported (see rasterizer.py)")
 
     def flat_params(self):
+        if self.fused_features:
+            return [self._xyz, self._features, self._opacity, self._scaling, self._rotation]
         return [self._xyz, self._features_dc, self._features_rest, self._opacity, self._scaling, self._rotation]

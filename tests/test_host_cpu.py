@@ -280,3 +280,19 @@ def test_flat_surfel_layout_matches_flatgrads_order():
     from vidu4d_b200.surfel_store import GROUPS
     assert [n for n, _ in GROUPS] == ["xyz", "f_dc", "f_rest", "opacity", "scaling", "rotation"]
     assert sum(k for _, k in GROUPS) == 58
+
+
+def test_surfel_cloud_fused_features_on_cpu():
+    """SurfelCloud(fused_features=True) keeps the SH rows as ONE leaf: get_features is that leaf (no torch.cat in the
+    graph), the values equal the reference-style pair's concatenation, and flat_params / FlatGrads follow the 5-tensor list."""
+    from vidu4d_b200 import distributed as D
+    from vidu4d_b200.synthetic import SurfelCloud, object_scene
+    scene = object_scene(257, seed=3)
+    a, b = SurfelCloud(scene, "cpu"), SurfelCloud(scene, "cpu", fused_features=True)
+    assert b.get_features is b._features and b.get_features.is_leaf and b.get_features.shape == (257, 16, 3)
+    assert not a.get_features.is_leaf and torch.equal(a.get_features.detach(), b.get_features.detach())
+    assert [tuple(p.shape) for p in b.flat_params()] == [(257, 3), (257, 16, 3), (257, 1), (257, 2), (257, 4)]
+    assert len(a.flat_params()) == 6
+    fg = D.FlatGrads(b.flat_params())
+    (b.get_features.sum() * 2.0 + b.get_xyz.sum()).backward()
+    assert fg.flat.numel() == 257 * 58 and float(fg.flat.sum()) == 257 * 48 * 2.0 + 257 * 3

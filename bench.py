@@ -10,6 +10,10 @@ backward, each frame a different camera), accumulates the surfel gradients, and 
 all-reduce of the flat gradient buffer (frames are the shard axis; weak scaling: per-GPU work is fixed).
 Ours: the F frames of a step are ONE batched launch set (sr_forward_batch / sr_backward_batch: every kernel has a frame
 dimension), captured in a CUDA graph; `--mode streams` keeps round 1's harness (F single-frame calls over S streams).
+Both arms of ours alternate between two captures of the step, so that the host checks step k-1 (overflow words; in the e2e
+arm also the loss read-back) only after it has queued step k.  In the value arm, for N > 1, step k's all-reduce runs on a
+communication stream under step k+1's compute (each capture owns its flat gradient buffer) and a step's timed interval
+ends only once the previous step's all-reduce is complete; in the e2e arm the all-reduce feeds the optimizer and is serial.
 
 One JSON line (rank 0):
   value       frames/s over all ranks, inputs resident in HBM, C-ABI calls, device-event timed (max over ranks)

@@ -121,3 +121,101 @@ def test_stage3_loss_oracle_gradients_match_finite_differences():
         cp_[c, y, x] += h; cn[c, y, x] -= h
         fd = (po.stage3_losses(cp_, am, *args, **kw)[0] - po.stage3_losses(cn, am, *args, **kw)[0]) / (2 * h)
         assert abs(fd - gc[c, y, x]) <= 1e-9 + 1e-4 * abs(fd)
+
+
+# ---- a float64 model of csrc/loss.cu's shared-memory tiling (32x8 tile + one-pixel ring, 80 ring threads, gather signs)
+# against the oracle on ragged image sizes: the index logic of the kernel, checked where the GPU tests use block-aligned
+# images.  The arithmetic is the oracle's; what is restated from the kernel is WHICH stencil lands in WHICH cell and who
+# reads it.
+def _loss_kernel_model(color, allmap, wvt, tanx, tany, depth_ratio, target, vis, mask_gt, mask_wt, w_rgb, w_mask, lam_n, lam_d):
+    """Python restatement of csrc/loss.cu:loss_grad_kernel's indexing: 32x8 tiles, sg[6][10][34] ring, 80 ring threads."""
+    _, H, W = color.shape
+    N = H * W
+    am = np.asarray(allmap, np.float64)
+    # surf_depth as loss_depth_kernel
+    med = po._nan_to_num00(am[5]); 
+    with np.errstate(all='ignore'):
+        ex = po._nan_to_num00((am[0] / am[1]))
+    sd = ex * (1 - depth_ratio) + depth_ratio * med
+    wv = np.asarray(wvt, np.float64)
+    R = wv[:3, :3]                      # c.R[i*3+j] = m[i*4+j]
+    B = wv[:3, :3].T                    # W2C rotation
+    A = np.linalg.inv(B)
+    fx, fy, cx, cy = W / (2 * tanx), H / (2 * tany), W * 0.5, H * 0.5
+    sN = lam_n / N
+    def ray(X, Y):
+        u, v = (X - cx) / fx, (Y - cy) / fy
+        return A @ np.array([u, v, 1.0])
+    def stencil_eval(X, Y, scale):
+        z = np.zeros(3)
+        if not (1 <= X < W - 1 and 1 <= Y < H - 1): return z, z, z
+        a_, b_, e_, f_ = ray(X, Y + 1), ray(X, Y - 1), ray(X + 1, Y), ray(X - 1, Y)
+        dD, dU, dR, dL = sd[Y + 1, X], sd[Y - 1, X], sd[Y, X + 1], sd[Y, X - 1]
+        dx = dD * a_ - dU * b_; dy = dR * e_ - dL * f_
+        n = np.cross(dx, dy); ln = np.linalg.norm(n)
+        a = am[1, Y, X]
+        sn = n * (a / max(ln, 1e-12))
+        g = scale * a * (R @ am[2:5, Y, X])
+        if ln > 1e-12:
+            w = n / ln; gn = (g - w * (w @ g)) / ln
+        else:
+            gn = g * 1e12
+        gdx = np.cross(dy, gn)          # dy x gn
+        gdy = np.cross(gn, dx)
+        return sn, gdx, gdy
+    g_allmap = np.zeros((8, H, W)); 
+    for by in range((H + 7) // 8):
+        for bx in range((W + 31) // 32):
+            sg = np.full((6, 10, 34), np.nan)
+            sn_own = {}
+            for t in range(256):
+                lx, ly = t & 31, t >> 5
+                x, y = bx * 32 + lx, by * 8 + ly
+                sn, gdx, gdy = stencil_eval(x, y, -sN)
+                sn_own[t] = sn
+                sg[0:3, ly + 1, lx + 1] = gdx; sg[3:6, ly + 1, lx + 1] = gdy
+                if t < 80:
+                    row = 0 if t < 32 else (9 if t < 64 else (t - 63 if t < 72 else t - 71))
+                    col = t + 1 if t < 32 else (t - 31 if t < 64 else (0 if t < 72 else 33))
+                    _, gdx, gdy = stencil_eval(bx * 32 + col - 1, by * 8 + row - 1, -sN)
+                    sg[0:3, row, col] = gdx; sg[3:6, row, col] = gdy
+            for t in range(256):
+                lx, ly = t & 31, t >> 5
+                x, y = bx * 32 + lx, by * 8 + ly
+                if not (x < W and y < H): continue
+                s = sn_own[t]
+                q = -sN * s
+                g_allmap[2:5, y, x] = R.T @ q
+                gp = sg[0:3, ly, lx + 1] - sg[0:3, ly + 2, lx + 1] + sg[3:6, ly + 1, lx] - sg[3:6, ly + 1, lx + 2]
+                assert np.isfinite(gp).all(), (bx, by, t)      # never reads an unwritten (corner) cell
+                gsd = gp @ ray(x, y)
+                gex, gmed = gsd * (1 - depth_ratio), gsd * depth_ratio
+                a, d0, m5 = am[1, y, x], am[0, y, x], am[5, y, x]
+                with np.errstate(all='ignore'):
+                    qq = d0 / a
+                qfin = np.isfinite(qq)
+                g_allmap[0, y, x] = gex / a if qfin else 0.0
+                g_acc = 0.0
+                if mask_gt is not None:
+                    g_acc += w_mask * 2 * (a - mask_gt[y, x]) * mask_wt[y, x] / N
+                g_allmap[1, y, x] = g_acc + (-gex * d0 / (a * a) if qfin else 0.0)
+                g_allmap[5, y, x] = gmed if np.isfinite(m5) else 0.0
+                g_allmap[6, y, x] = lam_d / N
+    return g_allmap
+
+
+
+@pytest.mark.parametrize("W,H,depth_ratio", [(70, 50, 0.0), (33, 9, 0.3), (5, 3, 1.0)])
+def test_loss_kernel_tiling_model_matches_oracle_on_ragged_sizes(W, H, depth_ratio):
+    rng = np.random.default_rng(W * 131 + H)
+    allmap = rng.uniform(0.2, 1.0, (8, H, W)); allmap[0] *= 3
+    allmap[5] = allmap[0] / allmap[1] + rng.normal(0, .05, (H, W)); allmap[2:5] = rng.normal(0, 1, (3, H, W))
+    color = rng.uniform(0, 1, (3, H, W)); target = rng.uniform(0, 1, (3, H, W))
+    vis = (rng.uniform(0, 1, (H, W)) > .2).astype(float); mg = (rng.uniform(0, 1, (H, W)) > .5).astype(float)
+    mw = rng.uniform(.5, 2, (H, W))
+    c, s = np.cos(0.3), np.sin(0.3)
+    W2C = np.eye(4); W2C[:3, :3] = np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]]); W2C[:3, 3] = [0.1, -0.2, 3.0]
+    kw = dict(w_rgb=0.8, w_mask=0.1, lambda_normal=0.05, lambda_dist=100.0)
+    _, ga = po.stage3_losses_backward(color, allmap, W2C.T, 0.5, 0.35, depth_ratio, target, vis, mg, mw, **kw)
+    mine = _loss_kernel_model(color, allmap, W2C.T, 0.5, 0.35, depth_ratio, target, vis, mg, mw, 0.8, 0.1, 0.05, 100.0)
+    assert np.abs(mine - ga).max() <= 1e-12 * np.abs(ga).max()
